@@ -1,0 +1,171 @@
+/*
+ * ldrones.h — C-ABI of libldrones.so, the B200 (sm_100a) population fitness
+ * evaluator for mbecker12/learning-drones.
+ *
+ * The reference has no FFI: its seam is the Python call
+ *     fly(drone, timesteps, delta_t, visualize, n_servers, punish_time,
+ *         reward_time, idx) -> (reward, real_time, idx)
+ * (reference flight/__init__.py:12-21,87,99), invoked once per drone per
+ * generation from evolve/evolution.py:64.  The entry points below are what a
+ * ctypes binding for that call site binds instead: one
+ * call evaluates the whole population.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in any signature.
+ *   - "device pointer" = address in the current CUDA device's global memory,
+ *     borrowed from the caller (e.g. torch.Tensor.data_ptr()); the library
+ *     never allocates, frees or retains caller buffers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ *     stream). *_device entry points are stream-ordered and asynchronous.
+ *   - every entry point returns 0 on success or a negative ld_status;
+ *     ld_last_error() returns a thread-local message for the last failure.
+ *     Nothing throws across the ABI.
+ *   - a "genome" is one drone's brain flattened exactly like the reference's
+ *     crossover does (evolve/util.py:58-59: layer.flatten(), layer after
+ *     layer): W1 (10x16) | W2 (10x11) | W3 (4x11), row = neuron, bias is the
+ *     LAST column (evolve/brain.py:45-46).  314 doubles = 2512 B per drone.
+ *     A population is the row-major matrix genomes[n][LD_GENOME_LEN].
+ */
+#ifndef LDRONES_H
+#define LDRONES_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LD_ABI_VERSION 1
+
+/* brain shape fixed by drone/drone.py:65 : NeuralNetwork({1:10, 2:10, 3:4}), n_inputs=15 */
+#define LD_N_IN 15
+#define LD_N_H1 10
+#define LD_N_H2 10
+#define LD_N_OUT 4
+#define LD_GENOME_LEN (LD_N_H1 * (LD_N_IN + 1) + LD_N_H2 * (LD_N_H1 + 1) + LD_N_OUT * (LD_N_H2 + 1)) /* 314 */
+
+/* PID mode: 18 gains per drone, order of choose_paramset.py:284-332
+ * (kp_x,kp_y,kp_z, ki_x,ki_y,ki_z, kd_x,kd_y,kd_z, kp_rol,kp_pit,kp_yaw,
+ *  ki_rol,ki_pit,ki_yaw, kd_rol,kd_pit,kd_yaw) */
+#define LD_PID_GAINS 18
+#define LD_PID_MAX_COINS 8
+
+/* final_state row: pos(3) vel(3) angle(3) angle_vel(3) acc_current(6) acc_last(6) thrust(4) */
+#define LD_STATE_LEN 28
+
+typedef enum ld_status {
+    LD_OK = 0,
+    LD_ERR_INVALID_ARG = -1, /* NULL pointer, negative size, bad params */
+    LD_ERR_CUDA = -2,        /* a CUDA runtime call failed; see ld_last_error() */
+    LD_ERR_NO_DEVICE = -3,   /* no usable sm_100 device */
+    LD_ERR_NCCL = -4
+} ld_status;
+
+/* status bits of ld_record.status */
+#define LD_STATUS_CRASHED 1   /* drone/drone.py:150-154 */
+#define LD_STATUS_NONFINITE 2 /* z became NaN: reference would raise in int(nan), drone.py:14 */
+
+/*
+ * Everything fly() reads that is not the brain.  Derived constants are
+ * computed by the HOST exactly the way the reference computes them (python
+ * floats), so the device never re-derives them with different rounding.
+ */
+typedef struct ld_params {
+    /* QuadcopterPhysics (drone/quadcopter/physical_model.py:53-73) */
+    double c_f;                /* coef_force   parameters.py:31 */
+    double c_m;                /* coef_moment  parameters.py:32 */
+    double r_m;                /* radius_motor_center */
+    double sqrt2_r_m;          /* np.sqrt(2) * r_m       physical_model.py:109 */
+    double inv_I[3];           /* 1/I_x, 1/I_y, 1/I_z    physical_model.py:63 */
+    double moments_payload[3]; /* physical_model.py:62,68-73 (zeros without payload) */
+    float neg_G32;             /* float32(-1 * G), G = gravity*(4 m_m + m_c) (+payload)  :61,101 */
+    float m_total32;           /* float32(m_c + 4 m_m + m_p)                             :114 */
+    float wind_cw32[3];        /* float32(wind) * float32(c_w)                           :103 */
+    float _pad0[3];
+    double dt;                 /* integrator step, drone/drone.py:10 (NOT fly()'s delta_t) */
+
+    /* initial state (parameters.py:47-52, Drone.__init__ / reset) */
+    double init_pos[3], init_vel[3], init_angle[3], init_angle_vel[3], init_thrust[4];
+
+    /* reward rules (drone/drone.py:12-17) and crash box (:150) */
+    double angle_limit;     /* pi/4 */
+    double angle_vel_limit; /* 20 */
+    double z_min, z_max;    /* crash iff z <= z_min or z > z_max : 0, 80 */
+    int32_t reward_time_passed;   /* 2 */
+    int32_t reward_crashed;       /* -3000 */
+    int32_t reward_unstable;      /* -1 */
+    int32_t reward_coin_distance; /* -100  (times int(distance)) */
+
+    /* coin schedule (flight/__init__.py:25,52) */
+    double coin0_pos[3];   /* (5,5,10) */
+    double coin_step[3];   /* (5,2.5,0) */
+    double coin0_radius;   /* 2 */
+    double coinN_radius;   /* 1 */
+    double coin0_thr2;     /* smallest s with sqrt(s) >= coin0_radius (host-computed; lets the
+                              device test ||d||^2 < thr2 instead of sqrt(||d||^2) < r, same truth value) */
+    double coinN_thr2;
+    int32_t coin0_value;   /* 2000 */
+    int32_t coinN_value;   /* 1000 */
+
+    double sigmoid_beta;   /* 0.4, evolve/brain.py:37 */
+
+    /* episode control (fly() arguments) */
+    int32_t timesteps;     /* 2500 default */
+    int32_t reward_time;   /* bool */
+    int32_t punish_time;   /* bool */
+    int32_t _pad1;
+} ld_params;
+
+/* what fly() leaves on the Drone besides its kinematic state */
+typedef struct ld_record {
+    int64_t reward;          /* drone.reward (python int) */
+    int32_t coins;           /* drone.coins */
+    int32_t flight_time;     /* drone.flight_time = number of loop iterations entered */
+    int32_t status;          /* LD_STATUS_* bits; bit0 == drone.crashed */
+    int32_t unstable;        /* number of -1 penalties applied (drone.py:159-164) */
+    double distance_to_coin; /* drone.distance_to_coin */
+} ld_record;
+
+/* ---- library ------------------------------------------------------------- */
+int ld_abi_version(void);
+const char* ld_last_error(void);
+/* number of CUDA devices usable by this build (compute capability 10.x); <0 on error */
+int ld_device_count(void);
+/* resident drones per launch wave on the current device (SMs x lanes per SM) */
+int64_t ld_wave_size(void);
+
+/* ---- MLP-controlled episode: replaces the population loop around fly() ----
+ * reference: evolve/evolution.py:64-73 calling flight/__init__.py:12-99 per drone.
+ *
+ * genomes      [n][LD_GENOME_LEN] doubles
+ * records      [n] ld_record                        (written)
+ * final_state  [n][LD_STATE_LEN] doubles or NULL    (written if not NULL)
+ * work_counter one int64 of scratch device memory used as the refill queue head
+ *              (the call zeroes it itself, stream-ordered)
+ */
+int ld_fly_mlp_f64_device(const ld_params* params, const double* genomes, int64_t n,
+                          ld_record* records, double* final_state,
+                          int64_t* work_counter, void* stream);
+
+/* Same computation with HOST buffers: copies in, runs, copies out, synchronises.
+ * This is the call the reference-facing plugin makes (bench e2e). Chunks the
+ * population so H2D copies overlap the kernel. */
+int ld_fly_mlp_f64_host(const ld_params* params, const double* genomes, int64_t n,
+                        ld_record* records, double* final_state);
+
+/* Debug tap: fly ONE drone and dump its state after every
+ * measure() call: trace[t][LD_STATE_LEN], t < timesteps; rows after the final
+ * step are left untouched. Device pointers. */
+int ld_fly_mlp_f64_trace_device(const ld_params* params, const double* genome,
+                                ld_record* record, double* trace, void* stream);
+
+/* ---- population statistics (warp-shuffle reductions) ----------------------
+ * stats[0]=sum flight_time (active drone-steps), [1]=max reward, [2]=argmax reward
+ * (lowest index wins ties, like np.argmax at evolve/evolution.py:77),
+ * [3]=sum coins, [4]=crashed count.  Device pointers. */
+int ld_reduce_records_device(const ld_record* records, int64_t n, int64_t* stats5, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDRONES_H */
