@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — drone-steps/s of the population fitness evaluation (fly() path) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--population survivors|random] [--drones-per-gpu D] [--timesteps H]
+
+A "step" is one pass of the hot path over one batch: every drone of the per-GPU population
+flies one H-timestep episode (one generation's fitness evaluation).  Workload at N=1 =
+BASELINE.json configs[2]: 65,536 synthetic drones, 2,000-step coin episode, the all-survivor
+(S) family of SURVEY.md §8d so that active == nominal drone-steps.  N>1 (torchrun, one rank
+per GPU): each rank flies its own 65,536-drone shard (weak scaling, drones are independent)
+and the fitness records are all-gathered with NCCL inside the timed step.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU algorithm
+(the C oracle port — the reference itself is pure Python and does not exist on the GPU box)
+on all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "drone-steps/sec (dynamics+brain+reward)"
+UNIT = "drone-steps/s"
+FLOP_PER_STEP = 850.0  # SURVEY.md §8d algorithmic work per drone-step (FMA = 2)
+GENOME_BYTES = 314 * 8
+RECORD_BYTES = 32
+
+
+def population(kind, n, seed=2026):
+    """The config-3 generators of SURVEY.md §8d (same formulas as oracle/gen_golden.py; the
+    golden fixtures are the first rows of exactly these arrays for seed 2026)."""
+    rng = np.random.default_rng(seed)
+    hover_bias = float(np.log(0.1962 / 0.8038) / 0.4)
+    # draw both families in the fixture's order so that prefixes match tests/golden
+    g_s = np.zeros((n, 314))
+    delta = rng.uniform(-0.010, 0.100, size=n)
+    for j in range(4):
+        g_s[:, 270 + j * 11 + 10] = hover_bias + delta
+    if kind == "survivors":
+        return g_s
+    cols = [rng.normal(0.0, 1.0 / np.sqrt(r), size=(n, r * c)) for r, c in ((10, 16), (10, 11), (4, 11))]
+    return np.concatenate(cols, axis=1)
+
+
+class ClockSampler:
+    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.2] or [r for _, r in self.rows]
+        if not rows:
+            return None
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        reasons = []
+        for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in rows):
+                reasons.append(name)
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][1]) if rows[0][1].isdigit() else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except OSError:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def cpu_baseline(kind, H, sample, threads=0):
+    """The reference's algorithm (C oracle port) on the host cores, bounded sample."""
+    from learning_drones_b200._abi import make_params
+    from oracle import oracle as O
+
+    g = population(kind, sample)
+    p = make_params(H)
+    O.fly_mlp(p, g[:64], nthreads=threads)  # warm
+    t0 = time.perf_counter()
+    rec, _ = O.fly_mlp(p, g, nthreads=threads)
+    dt = time.perf_counter() - t0
+    steps = int(rec["flight_time"].sum())
+    return steps / dt, steps, dt, (threads or O.max_threads())
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import oracle as O
+
+    cores = O.max_threads()
+    sample = args.cpu_sample or 8192
+    H = args.timesteps
+    for _ in range(args.warmup):
+        cpu_baseline(args.population, H, min(sample, 512))
+    t0 = time.perf_counter()
+    steps = 0
+    for _ in range(args.steps):
+        v, s, dt, cores = cpu_baseline(args.population, H, sample)
+        steps += s
+    total = time.perf_counter() - t0
+    value = steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"configs[2]: {args.drones_per_gpu}-drone {args.population} population, {H}-step coin episode",
+                   "population": args.population, "timesteps": H, "drones_per_gpu": args.drones_per_gpu},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} drones x {H} steps per step (first rows of the workload population), "
+                                   f"C restatement oracle/ld_oracle.c on {cores} threads; the pure-Python reference "
+                                   f"itself runs at ~4.7e3 drone-steps/s/core (BASELINE.md)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--population", default="survivors", choices=["survivors", "random"])
+    ap.add_argument("--drones-per-gpu", type=int, default=65536)
+    ap.add_argument("--timesteps", type=int, default=2000)
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from learning_drones_b200 import _lib, population as ldpop
+    from learning_drones_b200._abi import RECORD_DTYPE, make_params
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.load()
+
+    D, H = args.drones_per_gpu, args.timesteps
+    params = make_params(H)
+    # every rank flies its own shard of the global population [rank*D, (rank+1)*D)
+    host_genomes = population(args.population, D * world)[rank * D:(rank + 1) * D]
+    pinned = torch.from_numpy(np.ascontiguousarray(host_genomes)).pin_memory()
+    genomes = pinned.to(dev)
+    records = torch.empty((D, 4), dtype=torch.int64, device=dev)
+    counter = torch.empty(1, dtype=torch.int64, device=dev)
+    gathered = torch.empty((world * D, 4), dtype=torch.int64, device=dev) if world > 1 else None
+
+    def step():
+        ldpop.fly_population_device(genomes, params, records=records, work_counter=counter)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, records)  # fitness allgather for selection (NCCL/NVLink)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # ---- device-resident timing (value): K steps, CUDA events on the launching stream ----------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e_all0.record()
+    for a, b in ev:
+        a.record()
+        ldpop.fly_population_device(genomes, params, records=records, work_counter=counter)
+        b.record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, records)
+    e_all1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    total_ms = e_all0.elapsed_time(e_all1)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    rec_np = ldpop.records_to_numpy(records)
+    active_steps_rank = int(rec_np["flight_time"].sum())
+    act = torch.tensor([active_steps_rank], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(act)
+    active_steps = int(act.item())  # per step, whole job
+    value = active_steps * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host C-ABI call (pinned host buffers, copies inside) ----------
+    out_pinned = torch.empty((D, 4), dtype=torch.int64).pin_memory()
+    out_np = out_pinned.numpy().view(RECORD_DTYPE).reshape(-1)
+    host_np = pinned.numpy()
+    ldpop.fly_population_host(host_np, params, out=out_np)  # warm (allocates the workspace)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ldpop.fly_population_host(host_np, params, out=out_np)
+        _ = int(out_np["reward"].max())  # the step's result is read on the host
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    assert out_np.tobytes() == rec_np.tobytes(), "host-API result differs from device-API result"
+    e2e_value = active_steps * args.steps / e2e_s
+
+    if rank == 0:
+        peaks, peaks_src = measured_peaks()
+        tf = __import__("ctypes").c_double()
+        per_clk = __import__("ctypes").c_double()
+        _lib.check(L.ld_measure_fp64_peak(tf, per_clk))
+        alg_bytes = D * (GENOME_BYTES + RECORD_BYTES)  # per launch: genome rows in, records out
+        achieved_gbs = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        steps_per_launch = active_steps / world
+        fp64_tf = steps_per_launch * FLOP_PER_STEP / (kernel_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"configs[2]: {D}-drone {args.population} population per GPU, {H}-step coin episode, "
+                                   "batched fitness eval" + (" + NCCL all-gather of fitness records" if world > 1 else ""),
+                       "population": args.population, "timesteps": H, "drones_per_gpu": D, "global_drones": D * world,
+                       "active_drone_steps_per_step": active_steps, "nominal_drone_steps_per_step": D * world * H,
+                       "l2": f"inputs larger than L2 ({D * GENOME_BYTES / 1e6:.0f} MB genome matrix per GPU re-read every step)",
+                       "parallelism": f"population sharded over {world} GPU(s), no data-path collective; records all-gathered"},
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks_src,
+                         "kernel": "fly_mlp_f64_kernel", "kernel_ms": kernel_ms,
+                         "note": "compute-bound by construction (SURVEY §8d): 2,544 algorithmic bytes per 2,000-step "
+                                 "episode; the binding roofline is the fp64 pipe, see fp64_roofline"},
+            "fp64_roofline": {"bound": "fp64 FMA pipe (non-tensor)", "achieved": fp64_tf, "peak": tf.value, "unit": "TFLOP/s",
+                              "frac": fp64_tf / tf.value, "flop_per_drone_step": FLOP_PER_STEP,
+                              "peak_source": "ld_measure_fp64_peak (DFMA-chain microbenchmark, this run)",
+                              "dfma_per_clk_per_sm": per_clk.value},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": D * GENOME_BYTES * world,
+                    "d2h_bytes_per_step": D * RECORD_BYTES * world, "api": "ld_fly_mlp_f64_host via fly_population_host"},
+            "gpu_launches": args.steps * world,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            sample = args.cpu_sample or 8192
+            v, s, dt, cores = cpu_baseline(args.population, H, sample)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{sample} drones x {H} steps ({s} active drone-steps, {dt:.1f} s) of the same "
+                                              f"population; C restatement of the reference on {cores} threads"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

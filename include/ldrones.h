@@ -165,6 +165,14 @@ int ld_fly_mlp_f64_trace_device(const ld_params* params, const double* genome,
  * [3]=sum coins, [4]=crashed count.  Device pointers. */
 int ld_reduce_records_device(const ld_record* records, int64_t n, int64_t* stats5, void* stream);
 
+/* Roofline denominator: measured fp64 (non-tensor) FMA throughput of the current device in
+ * TFLOP/s (FMA = 2 flop), from a register-only DFMA-chain microbenchmark; optionally the same
+ * as DFMA per max-clock cycle per SM. */
+int ld_measure_fp64_peak(double* tflops_out, double* dfma_per_clk_per_sm_out);
+
+/* frees the device workspace that ld_fly_mlp_f64_host keeps between calls (per host thread) */
+void ld_release_workspace(void);
+
 #ifdef __cplusplus
 }
 #endif

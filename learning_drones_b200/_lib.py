@@ -1,0 +1,74 @@
+"""ctypes binding of libldrones.so (include/ldrones.h).
+
+There is NO fallback: if the shared library is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+from ._abi import LD_ABI_VERSION, LdParams, LdRecord
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libldrones.so")
+
+# every symbol include/ldrones.h declares
+EXPORTS = (
+    "ld_abi_version",
+    "ld_last_error",
+    "ld_device_count",
+    "ld_wave_size",
+    "ld_fly_mlp_f64_device",
+    "ld_fly_mlp_f64_host",
+    "ld_fly_mlp_f64_trace_device",
+    "ld_reduce_records_device",
+    "ld_release_workspace",
+    "ld_measure_fp64_peak",
+)
+
+
+class LdError(RuntimeError):
+    """A libldrones entry point returned a negative ld_status."""
+
+    def __init__(self, code, message):
+        super().__init__(f"libldrones error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libldrones.so (built in-tree by learning_drones_b200.build). Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m learning_drones_b200.build` "
+            "(nvcc, sm_100a). learning_drones_b200 has no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, dp, i64 = C.c_void_p, C.c_void_p, C.c_int64
+    L.ld_abi_version.restype = C.c_int
+    L.ld_last_error.restype = C.c_char_p
+    L.ld_device_count.restype = C.c_int
+    L.ld_wave_size.restype = C.c_int64
+    L.ld_fly_mlp_f64_device.argtypes = [C.POINTER(LdParams), dp, i64, vp, dp, vp, vp]
+    L.ld_fly_mlp_f64_device.restype = C.c_int
+    L.ld_fly_mlp_f64_host.argtypes = [C.POINTER(LdParams), dp, i64, vp, dp]
+    L.ld_fly_mlp_f64_host.restype = C.c_int
+    L.ld_fly_mlp_f64_trace_device.argtypes = [C.POINTER(LdParams), dp, vp, dp, vp]
+    L.ld_fly_mlp_f64_trace_device.restype = C.c_int
+    L.ld_reduce_records_device.argtypes = [vp, i64, vp, vp]
+    L.ld_reduce_records_device.restype = C.c_int
+    L.ld_release_workspace.restype = None
+    L.ld_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.ld_measure_fp64_peak.restype = C.c_int
+    if L.ld_abi_version() != LD_ABI_VERSION:
+        raise ImportError(f"libldrones ABI {L.ld_abi_version()} != python binding {LD_ABI_VERSION}; rebuild")
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != 0:
+        raise LdError(rc, load().ld_last_error().decode(errors="replace"))

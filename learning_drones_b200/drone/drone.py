@@ -1,0 +1,114 @@
+"""Drone — state / brain / reward container with the reference's attribute names
+(drone/drone.py:20-76,167-218).  The physics, integrator, controller and reward rules that the
+reference implements in Drone.measure / translate_input_to_thrust run inside the CUDA episode
+kernel; fly() (learning_drones_b200.flight) writes the outcome back onto these attributes.
+
+Differences from the reference, on purpose: no DataHandler is constructed (the reference's
+constructor creates ./evolution/<timestamp>/ on disk, data_scraper.py:58-66) and there is no
+visualisation socket.
+"""
+import numpy as np
+
+from .._abi import (  # noqa: F401  (re-exported constants of drone/drone.py:10-17)
+    ANGLE_LIMIT,
+    ANGLE_VEL_LIMIT,
+    REWARD_CRASHED,
+    REWARD_TIME_PASSED,
+    REWARD_UNSTABLE,
+    STATE_LEN,
+)
+from ..evolve.brain import NeuralNetwork
+from .quadcopter import parameters as P
+
+delta_t = 0.01
+REWARD_COIN_DISTANCE = lambda d: -100 * int(d)  # noqa: E731
+
+
+class Sensor:
+    """Per-DOF integrator state (reference drone/sensor/sensor.py:25-31); filled in by fly()."""
+
+    def __init__(self, delta_t, previous_pos, previous_vel, verbose=False):
+        self.current_acceleration = 0.0
+        self.last_acceleration = 0.0
+        self.previous_pos = previous_pos
+        self.previous_vel = previous_vel
+        self.delta_t = delta_t
+        self.verbose = verbose
+
+
+def _col(v, n):
+    return np.array(v, dtype=np.float64).reshape(n, 1)
+
+
+class Drone:
+    def __init__(
+        self,
+        port: int = 65432,
+        visualize=False,
+        n_servers=0,
+        initial_pos=None,
+        initial_vel=None,
+        initial_angle=None,
+        initial_angle_vel=None,
+    ):
+        if visualize or n_servers:
+            raise NotImplementedError("the B200 fitness path is headless (visualize=False, n_servers=0)")
+        self.port = port
+        self._initial = dict(
+            pos=_col(P.initial_pos if initial_pos is None else initial_pos, 3),
+            vel=_col(P.initial_vel if initial_vel is None else initial_vel, 3),
+            angle=_col(P.initial_angle if initial_angle is None else initial_angle, 3),
+            angle_vel=_col(P.initial_angle_vel if initial_angle_vel is None else initial_angle_vel, 3),
+        )
+        self.controller = NeuralNetwork(layer_spec={1: 10, 2: 10, 3: 4})
+        self.reset()
+
+    # reference drone/drone.py:177-218 (always resets to the module-level initial state)
+    def reset(self):
+        self.distance_to_coin = np.inf
+        self.reward = 0
+        self.crashed = False
+        self.coins = 0
+        self.flight_time = 0
+        self.position = _col(P.initial_pos, 3)
+        self.velocity = _col(P.initial_vel, 3)
+        self.angle = _col(P.initial_angle, 3)
+        self.angle_vel = _col(P.initial_angle_vel, 3)
+        self.thrust = _col(P.initial_thrust, 4)
+        self.sensors = [Sensor(delta_t, self.position[i, 0], self.velocity[i, 0]) for i in range(3)]
+        self.sensors += [Sensor(delta_t, self.angle[i, 0], self.angle_vel[i, 0]) for i in range(3)]
+
+    def reset_reward(self):
+        self.reward = 0
+
+    # reference drone/drone.py:167-172 — same draws from the global numpy stream, in the same order
+    def mutate(self, mutation_rate):
+        for i, layer in enumerate(self.controller.weights):
+            for j, row in enumerate(layer):
+                for k, _ in enumerate(row):
+                    if np.random.random_sample() < mutation_rate:
+                        self.controller.weights[i][j][k] += np.random.normal(0.0, 0.3)
+
+    # -- used by flight.fly -------------------------------------------------------------------
+    def start_state(self):
+        """State an episode starts from: whatever the attributes currently hold, as in the
+        reference where fly() continues from the Drone's state (fresh after __init__/reset())."""
+        if self.flight_time == 0 and self.reward == 0 and self.coins == 0:
+            return self.position, self.velocity, self.angle, self.angle_vel, self.thrust
+        raise RuntimeError("fly() on a Drone that already flew: call drone.reset() first (evolve/evolution.py:91-92)")
+
+    def load_result(self, record, state_row):
+        self.reward = int(record["reward"])
+        self.coins = int(record["coins"])
+        self.flight_time = int(record["flight_time"])
+        self.crashed = bool(record["status"] & 1)
+        self.distance_to_coin = float(record["distance_to_coin"])
+        s = np.asarray(state_row, dtype=np.float64).reshape(STATE_LEN)
+        self.position, self.velocity = s[0:3].reshape(3, 1).copy(), s[3:6].reshape(3, 1).copy()
+        self.angle, self.angle_vel = s[6:9].reshape(3, 1).copy(), s[9:12].reshape(3, 1).copy()
+        self.thrust = s[24:28].reshape(4, 1).copy()
+        pos = np.concatenate([s[0:3], s[6:9]])
+        vel = np.concatenate([s[3:6], s[9:12]])
+        for i, sensor in enumerate(self.sensors):
+            sensor.previous_pos, sensor.previous_vel = float(pos[i]), float(vel[i])
+            sensor.current_acceleration, sensor.last_acceleration = float(s[12 + i]), float(s[18 + i])

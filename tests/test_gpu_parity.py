@@ -1,0 +1,197 @@
+"""GPU parity tests: the CUDA episode kernel (through the C-ABI) against the reference fixtures
+and the CPU oracle.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+from _parity import COND_ROBUST, SET_STATE_FRAC, SETS, check_records, conditioning, state_dev  # noqa
+from learning_drones_b200._abi import GENOME_LEN, RECORD_DTYPE, STATE_LEN, make_params
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pop():
+    from learning_drones_b200 import population
+
+    return population
+
+
+@pytest.fixture(scope="module")
+def gen():
+    from oracle import gen_golden
+
+    return gen_golden
+
+
+@pytest.mark.parametrize("name,kw,min_robust", SETS)
+def test_kernel_matches_reference_fixture(pop, oracle, golden, name, kw, min_robust):
+    g = golden(name)
+    p = make_params(int(g["timesteps"]), **kw)
+    cond = conditioning(oracle, p, g["genomes"])
+    rec, state = pop.fly_population_host(g["genomes"], p, want_state=True)
+    robust = check_records(rec, state, g, cond, SET_STATE_FRAC.get(name))
+    assert robust.mean() >= min_robust
+
+
+@pytest.mark.parametrize("family,n,H", [("survivors", 4096, 2000), ("random", 4096, 2000), ("random", 20000, 2500)])
+def test_kernel_matches_oracle_subsample(pop, oracle, gen, family, n, H):
+    """parity on a subsample of the config-3 populations against the CPU oracle."""
+    rng = np.random.default_rng(2026)
+    s = gen.survivors(65536, rng)
+    r = gen.random_brains(65536, rng)
+    genomes = (s if family == "survivors" else r)[:n] if n <= 65536 else None
+    p = make_params(H)
+    cond = conditioning(oracle, p, genomes)
+    ref, ref_state = oracle.fly_mlp(p, genomes, want_state=True)
+    rec, state = pop.fly_population_host(genomes, p, want_state=True)
+    g = dict(reward=ref["reward"], coins=ref["coins"], flight_time=ref["flight_time"], status=ref["status"],
+             distance_to_coin=ref["distance_to_coin"], state=ref_state)
+    robust = check_records(rec, state, g, cond, SET_STATE_FRAC.get(name))
+    assert robust.mean() > 0.98
+    # the ill-conditioned remainder may differ, but only rarely
+    same = (rec["reward"] == ref["reward"]) & (rec["flight_time"] == ref["flight_time"])
+    assert same.mean() > 0.995
+
+
+def test_trace_matches_oracle(pop, oracle, golden):
+    for name in ("seed0_single", "hover_2000"):
+        g = golden(name)
+        p = make_params(int(g["timesteps"]))
+        rec, tr = pop.trace_drone(g["genomes"][0], p)
+        orec, otr = oracle.trace_mlp(p, g["genomes"][0])
+        n = int(orec["flight_time"])
+        assert int(rec["flight_time"]) == n == g["trace0"].shape[0]
+        assert int(rec["reward"]) == int(orec["reward"]) == int(g["reward"][0])
+        np.testing.assert_allclose(tr, otr[:n], rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(tr, g["trace0"], rtol=1e-7, atol=1e-9)
+        assert tr[0, 14] == otr[0, 14]  # float32 fingerprint of step 0 is bit-exact
+
+
+def test_device_api_equals_host_api(pop, gen):
+    import torch
+
+    rng = np.random.default_rng(7)
+    genomes = gen.random_brains(5000, rng)
+    p = make_params(600)
+    rec_h, st_h = pop.fly_population_host(genomes, p, want_state=True)
+    gt = torch.from_numpy(genomes).cuda()
+    rec_d, st_d = pop.fly_population_device(gt, p, want_state=True)
+    assert pop.records_to_numpy(rec_d).tobytes() == rec_h.tobytes()
+    assert st_d.cpu().numpy().tobytes() == st_h.tobytes()
+    # deterministic: a second launch (different lane/queue interleaving) gives identical bytes
+    rec_d2, _ = pop.fly_population_device(gt, p)
+    assert torch.equal(rec_d, rec_d2)
+    # permutation invariance: drones are independent
+    perm = rng.permutation(len(genomes))
+    rec_p, _ = pop.fly_population_host(genomes[perm], p)
+    assert rec_p.tobytes() == rec_h[perm].tobytes()
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 33, 95, 97, 14207, 14209])
+def test_ragged_population_sizes(pop, oracle, gen, n):
+    rng = np.random.default_rng(100 + n)
+    genomes = gen.random_brains(max(n, 1), rng)[:n]
+    p = make_params(400)
+    rec, st = pop.fly_population_host(genomes, p, want_state=True)
+    assert rec.shape == (n,) and st.shape == (n, STATE_LEN)
+    if n:
+        ref, _ = oracle.fly_mlp(p, genomes)
+        cond = conditioning(oracle, p, genomes)
+        ok = cond < COND_ROBUST
+        assert rec["reward"][ok].tolist() == ref["reward"][ok].tolist()
+        assert rec["flight_time"][ok].tolist() == ref["flight_time"][ok].tolist()
+
+
+def test_zero_timesteps_and_flags(pop, oracle, gen):
+    rng = np.random.default_rng(3)
+    genomes = gen.random_brains(200, rng)
+    for kw in (dict(timesteps=0), dict(timesteps=1), dict(timesteps=300, reward_time=False),
+               dict(timesteps=300, punish_time=True), dict(timesteps=300, punish_time=True, reward_time=False)):
+        p = make_params(**kw)
+        rec, st = pop.fly_population_host(genomes, p, want_state=True)
+        ref, rst = oracle.fly_mlp(p, genomes, want_state=True)
+        cond = conditioning(oracle, p, genomes)
+        ok = cond < COND_ROBUST
+        assert rec["reward"][ok].tolist() == ref["reward"][ok].tolist(), kw
+        assert rec["flight_time"][ok].tolist() == ref["flight_time"][ok].tolist(), kw
+        assert state_dev(st[ok], rst[ok]).max() < 1e-6
+
+
+def test_wind_and_payload(pop, oracle, gen):
+    rng = np.random.default_rng(5)
+    genomes = gen.random_brains(512, rng)
+    p = make_params(500, wind_speed=[0.5, -2.0, 0.25], mass_payload=0.05, x_payload=0.01, y_payload=-0.02)
+    rec, st = pop.fly_population_host(genomes, p, want_state=True)
+    ref, rst = oracle.fly_mlp(p, genomes, want_state=True)
+    cond = conditioning(oracle, p, genomes)
+    g = dict(reward=ref["reward"], coins=ref["coins"], flight_time=ref["flight_time"], status=ref["status"],
+             distance_to_coin=ref["distance_to_coin"], state=rst)
+    assert check_records(rec, st, g, cond).mean() > 0.95
+    # and it is not the no-wind result
+    rec0, _ = pop.fly_population_host(genomes, make_params(500))
+    assert (rec0["reward"] != rec["reward"]).any()
+
+
+def test_reduce_records(pop, gen):
+    import torch
+
+    rng = np.random.default_rng(9)
+    genomes = torch.from_numpy(gen.random_brains(30000, rng)).cuda()
+    rec, _ = pop.fly_population_device(genomes, make_params(500))
+    stats = pop.reduce_records(rec)
+    r = pop.records_to_numpy(rec)
+    assert stats["active_steps"] == int(r["flight_time"].sum())
+    assert stats["best_reward"] == int(r["reward"].max())
+    assert stats["best_index"] == int(np.argmax(r["reward"]))
+    assert stats["coins"] == int(r["coins"].sum())
+    assert stats["crashed"] == int((r["status"] & 1).sum())
+
+
+def test_full_size_properties(pop, gen):
+    """Config 3 at full size (65,536 x 2,000): size-independent invariants."""
+    import torch
+
+    rng = np.random.default_rng(2026)
+    s = gen.survivors(65536, rng)
+    p = make_params(2000)
+    gt = torch.from_numpy(s).cuda()
+    rec, _ = pop.fly_population_device(gt, p)
+    r = pop.records_to_numpy(rec)
+    assert (r["flight_time"] == 2000).all() and (r["status"] == 0).all()  # the (S) family survives
+    coins = r["coins"].astype(np.int64)
+    expect = (2 * r["flight_time"].astype(np.int64) + 2000 * (coins >= 1) + 1000 * np.maximum(coins - 1, 0)
+              - 3000 * (r["status"] & 1) - r["unstable"] - 100 * np.floor(r["distance_to_coin"]).astype(np.int64))
+    assert r["reward"].tolist() == expect.tolist()
+    assert len(np.unique(r["reward"])) > 20  # non-trivial fitness ranking
+    stats = pop.reduce_records(rec)
+    assert stats["active_steps"] == 65536 * 2000
+
+
+def test_fly_drop_in(golden):
+    """Reference-API call: fly(drone) on Drone objects (flight/__init__.py contract)."""
+    from learning_drones_b200.drone.drone import Drone
+    from learning_drones_b200.flight import fly, fly_population
+
+    g = golden("seed0_single")
+    np.random.seed(0)
+    d = Drone(visualize=False, n_servers=0)
+    # same global-RNG draws as the reference => same brain as the fixture
+    assert np.array_equal(d.controller.genome(), g["genomes"][0])
+    reward, real_time, idx = fly(d, idx=0)
+    assert (reward, real_time, idx) == (-4077, 1.69, 0)
+    assert isinstance(reward, int) and d.crashed and d.coins == 0 and d.flight_time == 170
+    assert d.distance_to_coin == pytest.approx(11.208182019123052, rel=1e-9)
+    np.testing.assert_allclose(d.position.ravel(), g["state"][0, :3], rtol=1e-7)
+    assert d.position.shape == (3, 1) and d.thrust.shape == (4, 1)
+    with pytest.raises(RuntimeError):
+        fly(d)  # needs reset(), like evolution.py does
+    d.reset()
+    assert fly(d, idx=5)[0] == -4077
+
+    g = golden("seed12345_gen0")
+    np.random.seed(12345)
+    drones = [Drone(visualize=False, n_servers=0) for _ in range(20)]
+    res = fly_population(drones)
+    assert [r[0] for r in res] == g["reward"].tolist()
+    assert [d.flight_time for d in drones] == g["flight_time"].tolist()
+    np.testing.assert_allclose([r[1] for r in res], g["real_time"])
