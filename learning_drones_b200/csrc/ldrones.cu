@@ -21,9 +21,11 @@ using namespace ld;
 
 constexpr int kWarpsPerCta = 3;
 constexpr int kCtaThreads = kWarpsPerCta * 32;
-constexpr int kSmemDoubles = kL1 + kL2;               // 270 per lane
-constexpr int kRowBytes = kSmemDoubles * 8;           // 2160
-constexpr int kSmemBytes = kCtaThreads * kRowBytes;   // 207360
+constexpr int kL3Smem = 32;                           // leading part of layer 3 that also fits in shared memory
+constexpr int kL3Regs = kL3 - kL3Smem;                // 12 trailing layer-3 weights stay in registers
+constexpr int kSmemDoubles = kL1 + kL2 + kL3Smem;     // 302 per lane
+constexpr int kRowBytes = kSmemDoubles * 8;           // 2416
+constexpr int kSmemBytes = kCtaThreads * kRowBytes;   // 231936 of the SM's 232448
 static_assert((kRowBytes / 16) % 2 == 1, "row stride must be an odd number of 16-B units (bank-conflict-free LDS.128)");
 static_assert(kL1 % 2 == 0 && kSmemDoubles % 2 == 0, "double2 staging");
 
@@ -61,7 +63,7 @@ __device__ __forceinline__ void write_state(const Drone& d, const double* a_last
 }
 
 // evolve/brain.py:56-76 on this lane's staged weights
-__device__ __forceinline__ void brain(Drone& d, const double2* __restrict__ wrow, const double (&w3)[kL3], double neg_beta,
+__device__ __forceinline__ void brain(Drone& d, const double2* __restrict__ wrow, const double (&w3)[kL3Regs], double neg_beta,
                                       bool keep_old) {
     double in[kIn];
 #pragma unroll
@@ -84,7 +86,7 @@ __device__ __forceinline__ void brain(Drone& d, const double2* __restrict__ wrow
     dense<kH2, kH1>([&](int i) { return smem_w(kL1 + i); }, h1, h2);
 #pragma unroll
     for (int j = 0; j < kH2; ++j) h2[j] = relu(h2[j]);
-    dense<kOut, kH2>([&](int i) { return w3[i]; }, h2, out);
+    dense<kOut, kH2>([&](int i) { return i < kL3Smem ? smem_w(kL1 + kL2 + (i < kL3Smem ? i : 0)) : w3[i >= kL3Smem ? i - kL3Smem : 0]; }, h2, out);
 #pragma unroll
     for (int j = 0; j < kOut; ++j) {
         const double th = sigmoid_fast(out[j], neg_beta);
@@ -94,6 +96,31 @@ __device__ __forceinline__ void brain(Drone& d, const double2* __restrict__ wrow
 }
 
 enum Mode { kPlain = 0, kState = 1, kTrace = 2 };
+
+// flight/__init__.py:83-87,97-99: terminal distance penalty, then publish the drone's outcome
+template <int MODE>
+__device__ __forceinline__ void publish(const ld_params& p, Drone& d, const double* a_last, long long idx,
+                                        ld_record* __restrict__ records, double* __restrict__ final_state) {
+    double dist;
+    const long long reward = finish(p, d, dist);
+    // 32-B record = two 16-B stores
+    int4 lo, hi;
+    lo.x = (int)(unsigned)(reward & 0xffffffffLL);
+    lo.y = (int)(reward >> 32);
+    lo.z = d.coins;
+    lo.w = d.flight_time;
+    hi.x = d.status;
+    hi.y = d.unstable;
+    hi.z = __double2loint(dist);
+    hi.w = __double2hiint(dist);
+    int4* out = reinterpret_cast<int4*>(records + idx);
+    out[0] = lo;
+    out[1] = hi;
+    if (MODE != kPlain) {
+        if (final_state) write_state(d, a_last, final_state + idx * LD_STATE_LEN);
+    }
+}
+
 
 // One population evaluation = the loop of evolve/evolution.py:64-73 around flight/__init__.py:fly().
 // MODE kState: also write the final kinematic state; kTrace: n == 1, dump the state after every
@@ -114,9 +141,9 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
 
     Drone d;
     drone_reset(p, d);
-    double w3[kL3];
+    double w3[kL3Regs];
 #pragma unroll
-    for (int i = 0; i < kL3; ++i) w3[i] = 0.0;
+    for (int i = 0; i < kL3Regs; ++i) w3[i] = 0.0;
     long long idx = -1; // drone this lane is flying; -1 = idle
     int t = 0;
     bool more = true; // queue not yet exhausted (warp-uniform)
@@ -137,7 +164,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
 #pragma unroll 9
                     for (int i = 0; i < kSmemDoubles / 2; ++i) wrow[i] = __ldg(src + i);
 #pragma unroll
-                    for (int i = 0; i < kL3 / 2; ++i) {
+                    for (int i = 0; i < kL3Regs / 2; ++i) {
                         const double2 w = __ldg(src + kSmemDoubles / 2 + i);
                         w3[2 * i] = w.x;
                         w3[2 * i + 1] = w.y;
@@ -151,9 +178,17 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
         }
         if (__ballot_sync(0xffffffffu, idx >= 0) == 0u) break;
 
+        if (H <= 0) { // fly(timesteps=0): the loop body never runs (warp-uniform, cold)
+            if (idx >= 0) {
+                const double zeros[6] = {0, 0, 0, 0, 0, 0};
+                publish<MODE>(p, d, zeros, idx, records, final_state);
+                idx = -1;
+            }
+            continue;
+        }
         // ---- one timestep of flight/__init__.py:39-93 ------------------------------------------
         const bool flying = idx >= 0;
-        const bool live = flying && t < H; // H == 0: no loop iteration at all
+        const bool live = flying;
         double a_last[6];
         int u;
         step_rewards_and_coin(p, d, live, time_reward);
@@ -175,30 +210,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
         }
         t += live ? 1 : 0;
         if (flying && (crashed || t >= H)) {
-            double dist;
-            const long long reward = finish(p, d, dist);
-            // 32-B record = two 16-B stores
-            int4 lo, hi;
-            lo.x = (int)(unsigned)(reward & 0xffffffffLL);
-            lo.y = (int)(reward >> 32);
-            lo.z = d.coins;
-            lo.w = d.flight_time;
-            hi.x = d.status;
-            hi.y = d.unstable;
-            hi.z = __double2loint(dist);
-            hi.w = __double2hiint(dist);
-            int4* out = reinterpret_cast<int4*>(records + idx);
-            out[0] = lo;
-            out[1] = hi;
-            if (MODE != kPlain) {
-                if (H == 0) {
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) a_last[i] = 0.0;
-                }
-                // the reference leaves the thrust of the last brain call on the Drone; on the final
-                // step of a crash no brain call happened (flight/__init__.py:80-87)
-                if (final_state) write_state(d, a_last, final_state + idx * LD_STATE_LEN);
-            }
+            publish<MODE>(p, d, a_last, idx, records, final_state);
             idx = -1;
         }
     }

@@ -46,7 +46,7 @@ def test_kernel_matches_oracle_subsample(pop, oracle, gen, family, n, H):
     rec, state = pop.fly_population_host(genomes, p, want_state=True)
     g = dict(reward=ref["reward"], coins=ref["coins"], flight_time=ref["flight_time"], status=ref["status"],
              distance_to_coin=ref["distance_to_coin"], state=ref_state)
-    robust = check_records(rec, state, g, cond, SET_STATE_FRAC.get(name))
+    robust = check_records(rec, state, g, cond)
     assert robust.mean() > 0.98
     # the ill-conditioned remainder may differ, but only rarely
     same = (rec["reward"] == ref["reward"]) & (rec["flight_time"] == ref["flight_time"])
