@@ -1,12 +1,13 @@
 // ldrones.cu — libldrones.so: sm_100a kernels + the C-ABI of include/ldrones.h.
 //
 // Episode kernel layout:
-//   * persistent grid, one CTA of 3 warps per SM; one drone per lane, its whole episode in
-//     registers; lanes pull the next drone from a global queue head when theirs ends.
-//   * each lane's brain: layers 1+2 (270 doubles) in its own shared-memory row of 2160 B
-//     (135 x 16 B: an odd number of 16-B units, so a warp's LDS.128 at a common row offset hits
-//     every bank group exactly once per quarter-warp), layer 3 (44 doubles) in registers.
-//     96 lanes x 2160 B = 202.5 KiB of the SM's 227 KiB.
+//   * persistent grid, one CTA of 4 warps per SM (one warp per SM sub-partition); one drone per
+//     lane, its whole episode in registers; lanes pull the next drone from a global queue head.
+//   * each lane's brain (314 fp64 weights) must be re-read every timestep and nothing else is: the
+//     kernel is bound by the per-sub-partition register-file fill rate (measured: ~40 B/clk/warp
+//     from shared memory, ~54 B/clk/warp from Tensor Memory).  256 weights per lane therefore sit
+//     in Tensor Memory (all 512 columns of the lane) and are streamed with tcgen05.ld, 58 in the
+//     lane's shared-memory row.
 //   * HBM traffic per drone-episode: its 2512-B genome row in, a 32-B record (+224-B state) out.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -19,15 +20,37 @@ namespace {
 
 using namespace ld;
 
-constexpr int kWarpsPerCta = 3;
-constexpr int kCtaThreads = kWarpsPerCta * 32;
-constexpr int kL3Smem = 32;                           // leading part of layer 3 that also fits in shared memory
-constexpr int kL3Regs = kL3 - kL3Smem;                // 12 trailing layer-3 weights stay in registers
-constexpr int kSmemDoubles = kL1 + kL2 + kL3Smem;     // 302 per lane
-constexpr int kRowBytes = kSmemDoubles * 8;           // 2416
-constexpr int kSmemBytes = kCtaThreads * kRowBytes;   // 231936 of the SM's 232448
+// ---- where one lane's 314 brain weights live ----------------------------------------------------
+// Stored order is k-major per layer (all neurons' weight for input k next to each other), so any
+// run of consecutive stored weights feeds up to 10 independent fma chains:
+//   s in [0,160)   : layer 1, s = k*10 + j      <-> genome[j*16 + k]
+//   s in [160,270) : layer 2, s-160 = k*10 + j  <-> genome[160 + j*11 + k]
+//   s in [270,314) : layer 3, s-270 = k*4 + j   <-> genome[270 + j*11 + k]
+// s < 256 sits in Tensor Memory: lane = the thread's TMEM lane, columns 2s (low word), 2s+1 (high
+// word); read per step as 16 tcgen05.ld.32x32b.x32 chunks of 16 doubles.  s >= 256 (58 doubles)
+// sits in this lane's 464-B shared-memory row (29 x 16 B: odd, bank-conflict-free LDS.128).
+constexpr int kWarpsPerCta = 4;                       // warp w owns TMEM lanes 32w..32w+31
+constexpr int kCtaThreads = kWarpsPerCta * 32;        // 128 drones resident per SM
+constexpr int kTmemCols = 512;                        // the whole Tensor Memory of the SM
+constexpr int kTmemDoubles = kTmemCols / 2;           // 256 weights per lane
+constexpr int kChunk = 16;                            // doubles per tcgen05.ld x32
+constexpr int kChunks = kTmemDoubles / kChunk;        // 16
+constexpr int kSmemDoubles = LD_GENOME_LEN - kTmemDoubles; // 58
+constexpr int kRowBytes = kSmemDoubles * 8;           // 464
+constexpr int kSmemUsed = kCtaThreads * kRowBytes;    // 59392
+// Tensor Memory is one allocation per SM: request more than half of the SM's shared memory so a
+// second CTA (e.g. of a concurrent launch on another stream) can never become resident next to us
+constexpr int kSmemBytes = 120 * 1024;
+static_assert(kSmemUsed <= kSmemBytes, "shared-memory rows");
+constexpr int kRefillBatch = 8;                       // idle lanes that trigger a refill
 static_assert((kRowBytes / 16) % 2 == 1, "row stride must be an odd number of 16-B units (bank-conflict-free LDS.128)");
-static_assert(kL1 % 2 == 0 && kSmemDoubles % 2 == 0, "double2 staging");
+static_assert(kSmemDoubles % 2 == 0, "double2 staging");
+
+__host__ __device__ constexpr int stored_to_genome(int s) {
+    return s < kL1 ? (s % kH1) * (kIn + 1) + s / kH1
+                   : s < kL1 + kL2 ? kL1 + ((s - kL1) % kH2) * (kH1 + 1) + (s - kL1) / kH2
+                                   : kL1 + kL2 + ((s - kL1 - kL2) % kOut) * (kH2 + 1) + (s - kL1 - kL2) / kOut;
+}
 
 thread_local char g_err[512] = "";
 
@@ -44,6 +67,52 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
         cudaError_t e_ = (call);                                        \
         if (e_ != cudaSuccess) return fail(LD_ERR_CUDA, #call, e_);     \
     } while (0)
+
+// ---- tcgen05 (Tensor Memory) wrappers -----------------------------------------------------------
+#define LD_R32(v, o) \
+    v[o + 0], v[o + 1], v[o + 2], v[o + 3], v[o + 4], v[o + 5], v[o + 6], v[o + 7], v[o + 8], v[o + 9], v[o + 10], v[o + 11], \
+    v[o + 12], v[o + 13], v[o + 14], v[o + 15], v[o + 16], v[o + 17], v[o + 18], v[o + 19], v[o + 20], v[o + 21], v[o + 22], \
+    v[o + 23], v[o + 24], v[o + 25], v[o + 26], v[o + 27], v[o + 28], v[o + 29], v[o + 30], v[o + 31]
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t (&v)[32], uint32_t taddr) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+
+// tcgen05.ld is asynchronous: the registers are valid only after wait::ld.  Passing them through
+// the wait as read-write operands gives the compiler a true dependency, so no consumer can be
+// scheduled above it.
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32(const uint32_t (&v)[32], uint32_t taddr) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        :
+        : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+          "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+          "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void write_state(const Drone& d, const double* a_last, double* row) {
 #pragma unroll
@@ -62,34 +131,82 @@ __device__ __forceinline__ void write_state(const Drone& d, const double* a_last
     for (int i = 0; i < 4; ++i) row[24 + i] = d.thrust[i];
 }
 
-// evolve/brain.py:56-76 on this lane's staged weights
-__device__ __forceinline__ void brain(Drone& d, const double2* __restrict__ wrow, const double (&w3)[kL3Regs], double neg_beta,
-                                      bool keep_old) {
+// evolve/brain.py:41-54, one stored weight at a time.  S is a compile-time stored index; every
+// neuron's sum is a k-ordered fma chain that starts with the k=0 product and ends with `+ bias`
+// (the trailing 1 of np.vstack((x, [[1]]))), followed by its activation.
+struct Mlp {
     double in[kIn];
+    double h1[kH1], h2[kH2], out[kOut];
+};
+
+template <int S>
+__device__ __forceinline__ void mlp_mac(Mlp& m, double w) {
+    if (S < kL1) {
+        constexpr int k = S / kH1, j = S % kH1;
+        if (k == 0) m.h1[j] = w * m.in[0];
+        else if (k < kIn) m.h1[j] = fma(w, m.in[k < kIn ? k : 0], m.h1[j]);
+        else m.h1[j] = relu(m.h1[j] + w);
+    } else if (S < kL1 + kL2) {
+        constexpr int t = S - kL1 >= 0 ? S - kL1 : 0, k = t / kH2, j = t % kH2;
+        if (k == 0) m.h2[j] = w * m.h1[0];
+        else if (k < kH1) m.h2[j] = fma(w, m.h1[k < kH1 ? k : 0], m.h2[j]);
+        else m.h2[j] = relu(m.h2[j] + w);
+    } else {
+        constexpr int t = S - kL1 - kL2 >= 0 ? S - kL1 - kL2 : 0, k = t / kOut, j = t % kOut;
+        if (k == 0) m.out[j] = w * m.h2[0];
+        else if (k < kH2) m.out[j] = fma(w, m.h2[k < kH2 ? k : 0], m.out[j]);
+        else m.out[j] = m.out[j] + w;
+    }
+}
+
+template <int C, int E = 0>
+__device__ __forceinline__ void mlp_chunk(Mlp& m, const uint32_t (&v)[32]) {
+    if constexpr (E < kChunk) {
+        mlp_mac<C * kChunk + E>(m, __hiloint2double((int)v[2 * E + 1], (int)v[2 * E]));
+        mlp_chunk<C, E + 1>(m, v);
+    }
+}
+
+template <int P = 0>
+__device__ __forceinline__ void mlp_smem_tail(Mlp& m, const double2* __restrict__ wrow) {
+    if constexpr (P < kSmemDoubles / 2) {
+        const double2 w = wrow[P];
+        mlp_mac<kTmemDoubles + 2 * P>(m, w.x);
+        mlp_mac<kTmemDoubles + 2 * P + 1>(m, w.y);
+        mlp_smem_tail<P + 1>(m, wrow);
+    }
+}
+
+// chunks C..15 with the next chunk's tcgen05.ld in flight while chunk C is consumed
+template <int C>
+__device__ __forceinline__ void mlp_tmem_chunks(Mlp& m, uint32_t taddr, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
+    if constexpr (C + 1 < kChunks) tmem_ld32(nxt, taddr + 32 * (C + 1));
+    mlp_chunk<C>(m, cur);
+    if constexpr (C + 1 < kChunks) {
+        tmem_wait_ld(nxt);
+        mlp_tmem_chunks<C + 1>(m, taddr, nxt, cur);
+    }
+}
+
+// evolve/brain.py:56-76 on this lane's staged weights (warp-converged: tcgen05.ld is .sync.aligned)
+__device__ __forceinline__ void brain(Drone& d, uint32_t taddr, const double2* __restrict__ wrow, double neg_beta, bool keep_old) {
+    Mlp m;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        in[i] = d.x[i];
-        in[3 + i] = d.v[i];
-        in[6 + i] = d.x[3 + i];
-        in[9 + i] = d.v[3 + i];
-        in[12 + i] = d.coin[i];
+        m.in[i] = d.x[i];
+        m.in[3 + i] = d.v[i];
+        m.in[6 + i] = d.x[3 + i];
+        m.in[9 + i] = d.v[3 + i];
+        m.in[12 + i] = d.coin[i];
     }
-    double h1[kH1], h2[kH2], out[kOut];
-    // weights are fetched as 16-B pairs (LDS.128); after unrolling every index is a constant
-    auto smem_w = [&](int i) {
-        const double2 w = wrow[i >> 1];
-        return (i & 1) ? w.y : w.x;
-    };
-    dense<kH1, kIn>([&](int i) { return smem_w(i); }, in, h1);
-#pragma unroll
-    for (int j = 0; j < kH1; ++j) h1[j] = relu(h1[j]);
-    dense<kH2, kH1>([&](int i) { return smem_w(kL1 + i); }, h1, h2);
-#pragma unroll
-    for (int j = 0; j < kH2; ++j) h2[j] = relu(h2[j]);
-    dense<kOut, kH2>([&](int i) { return i < kL3Smem ? smem_w(kL1 + kL2 + (i < kL3Smem ? i : 0)) : w3[i >= kL3Smem ? i - kL3Smem : 0]; }, h2, out);
+    uint32_t a[32], b[32];
+    tmem_ld32(a, taddr);
+    tmem_wait_ld(a);
+    mlp_tmem_chunks<0>(m, taddr, a, b);
+    mlp_smem_tail(m, wrow);
 #pragma unroll
     for (int j = 0; j < kOut; ++j) {
-        const double th = sigmoid_fast(out[j], neg_beta);
+        const double th = sigmoid_fast(m.out[j], neg_beta);
         // on the crash step the reference never reaches the brain (flight/__init__.py:80-87)
         d.thrust[j] = keep_old ? d.thrust[j] : th;
     }
@@ -121,19 +238,54 @@ __device__ __forceinline__ void publish(const ld_params& p, Drone& d, const doub
     }
 }
 
+// Stage the brains of the lanes in `fresh` (bit per lane): Tensor-Memory part by read-modify-write
+// of whole 16-double chunks (tcgen05.st writes all 32 lanes, so lanes in flight write back what
+// they read), shared-memory part by plain stores.  Warp-converged.
+template <int C = 0>
+__device__ __forceinline__ void stage_tmem(uint32_t taddr, bool mine_fresh, const double* __restrict__ row) {
+    if constexpr (C < kChunks) {
+        uint32_t v[32];
+        tmem_ld32(v, taddr + 32 * C);
+        tmem_wait_ld(v);
+        if (mine_fresh) {
+#pragma unroll
+            for (int e = 0; e < kChunk; ++e) {
+                const double w = __ldg(row + stored_to_genome(C * kChunk + e));
+                v[2 * e] = (uint32_t)__double2loint(w);
+                v[2 * e + 1] = (uint32_t)__double2hiint(w);
+            }
+        }
+        __syncwarp();
+        tmem_st32(v, taddr + 32 * C);
+        stage_tmem<C + 1>(taddr, mine_fresh, row);
+    }
+}
 
 // One population evaluation = the loop of evolve/evolution.py:64-73 around flight/__init__.py:fly().
 // MODE kState: also write the final kinematic state; kTrace: n == 1, dump the state after every
 // measure() (debug tap).  All 32 lanes execute every step (idle lanes run masked) so that the
-// step body is one straight-line block.
+// step body is one straight-line, warp-converged block.
 template <bool EXTRAS, int MODE>
 __global__ void __launch_bounds__(kCtaThreads, 1)
 fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict__ genomes, long long n,
                    ld_record* __restrict__ records, double* __restrict__ final_state,
                    unsigned long long* __restrict__ queue_head, double* __restrict__ trace) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t tmem_base_slot;
     double2* wrow = reinterpret_cast<double2*>(smem_raw + (size_t)threadIdx.x * kRowBytes);
-    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+
+    // the CTA owns the SM's whole Tensor Memory (512 columns x 128 lanes x 32 bit = 256 KiB)
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = tmem_base_slot;
+    const uint32_t taddr = tmem_base + ((warp * 32u) << 16); // this warp's lane quadrant, column 0
+
     const double neg_beta = -p.sigmoid_beta;
     const double rcp_m = 1.0 / (double)p.m_total32;
     const int time_reward = (p.reward_time ? p.reward_time_passed : 0) - (p.punish_time ? p.reward_time_passed : 0);
@@ -141,38 +293,41 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
 
     Drone d;
     drone_reset(p, d);
-    double w3[kL3Regs];
-#pragma unroll
-    for (int i = 0; i < kL3Regs; ++i) w3[i] = 0.0;
     long long idx = -1; // drone this lane is flying; -1 = idle
     int t = 0;
     bool more = true; // queue not yet exhausted (warp-uniform)
 
     for (;;) {
-        // ---- refill idle lanes from the queue (warp-aggregated fetch) -------------------------
+        // ---- refill idle lanes from the queue (warp-aggregated fetch, batched) -----------------
         const unsigned idle = __ballot_sync(0xffffffffu, idx < 0);
-        if (idle && more) {
+        if (more && (__popc(idle) >= kRefillBatch || idle == 0xffffffffu)) {
             unsigned long long base = 0;
             const int leader = __ffs(idle) - 1;
             if ((int)lane == leader) base = atomicAdd(queue_head, (unsigned long long)__popc(idle));
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (idx < 0) {
-                const long long mine = (long long)base + __popc(idle & ((1u << lane) - 1u));
-                if (mine < n) {
-                    idx = mine;
-                    const double2* __restrict__ src = reinterpret_cast<const double2*>(genomes + idx * LD_GENOME_LEN);
-#pragma unroll 9
-                    for (int i = 0; i < kSmemDoubles / 2; ++i) wrow[i] = __ldg(src + i);
+            const long long mine = (long long)base + __popc(idle & ((1u << lane) - 1u));
+            const bool fresh = idx < 0 && mine < n;
+            const double* __restrict__ row = genomes + (fresh ? mine : 0) * LD_GENOME_LEN;
+            if (fresh) {
+                // pull the 2512-B row into L1 with 20 independent loads; the gathers below then hit
+                unsigned touch = 0;
 #pragma unroll
-                    for (int i = 0; i < kL3Regs / 2; ++i) {
-                        const double2 w = __ldg(src + kSmemDoubles / 2 + i);
-                        w3[2 * i] = w.x;
-                        w3[2 * i + 1] = w.y;
-                    }
-                    drone_reset(p, d);
-                    t = 0;
+                for (int i = 0; i < LD_GENOME_LEN; i += 16) touch ^= (unsigned)__double2loint(__ldg(row + i));
+                if (touch == 0x9e3779b9u) wrow[0].x = 0.0; // keeps the loads alive; rewritten just below
+#pragma unroll
+                for (int i = 0; i < kSmemDoubles / 2; ++i) {
+                    double2 w;
+                    w.x = __ldg(row + stored_to_genome(kTmemDoubles + 2 * i));
+                    w.y = __ldg(row + stored_to_genome(kTmemDoubles + 2 * i + 1));
+                    wrow[i] = w;
                 }
+                idx = mine;
+                drone_reset(p, d);
+                t = 0;
             }
+            __syncwarp();
+            stage_tmem(taddr, fresh, row);
+            tmem_wait_st();
             more = (long long)base + __popc(idle) < n;
             trig_update(d); // warp-converged; recomputing it for lanes in flight is idempotent
         }
@@ -187,8 +342,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             continue;
         }
         // ---- one timestep of flight/__init__.py:39-93 ------------------------------------------
-        const bool flying = idx >= 0;
-        const bool live = flying;
+        const bool live = idx >= 0;
         double a_last[6];
         int u;
         step_rewards_and_coin(p, d, live, time_reward);
@@ -201,7 +355,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
         }
         // next step's trigonometry and this step's brain: independent, interleaved by the scheduler
         trig_update(d);
-        brain(d, wrow, w3, neg_beta, MODE != kPlain && crashed);
+        brain(d, taddr, wrow, neg_beta, MODE != kPlain && crashed);
         if (MODE == kTrace) {
             if (live && !crashed) {
 #pragma unroll
@@ -209,11 +363,16 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             }
         }
         t += live ? 1 : 0;
-        if (flying && (crashed || t >= H)) {
+        if (live && (crashed || t >= H)) {
             publish<MODE>(p, d, a_last, idx, records, final_state);
             idx = -1;
         }
     }
+
+    // every warp is done with its Tensor-Memory lanes before the allocation is returned
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
 }
 
 // ---- population statistics: warp-shuffle reductions -----------------------------------------
