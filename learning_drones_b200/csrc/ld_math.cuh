@@ -13,7 +13,7 @@
 //   exp    : k = rint(x log2 e), r = x - k ln2 (2-term), 1 + r + r^2 g(r) with a degree-9
 //            Chebyshev fit of g (|approximation error| < 0.15 ulp), scaled by 2^k in two halves
 //            so that overflow -> +inf and underflow -> 0/subnormal come out of the arithmetic.
-//   recip  : MUFU.RCP64H seed + 3 Newton steps; quotients by Markstein correction => the
+//   recip  : MUFU.RCP64H seed + 2 Newton steps; quotients by Markstein correction => the
 //            quotient is correctly rounded (IEEE division) for normal operands.
 #pragma once
 #include <cuda_runtime.h>
@@ -21,6 +21,19 @@
 namespace ld {
 
 constexpr double kTrigFastMax = 105615.0;
+
+// Polynomial coefficients live in constant memory: a DFMA can take its addend straight from the
+// constant bank, whereas literals are rebuilt with two 32-bit moves per use inside the hot loop.
+__constant__ double kSinC[6] = {1.58969099521155010221e-10,  -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+                                -1.98412698298579493134e-04, 8.33333333332248946124e-03,  -1.66666666666666324348e-01};
+__constant__ double kCosC[6] = {-1.13596475577881948265e-11, 2.08757232129817482790e-09,  -2.75573143513906633035e-07,
+                                2.48015872894767294178e-05,  -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+__constant__ double kExpC[10] = {2.5100424157005067e-08, 2.7620138719733994e-07, 2.7557268378684192e-06, 2.480152119021773e-05,
+                                 0.00019841269863105968, 0.0013888888917281794,  0.008333333333330051,   0.04166666666662399,
+                                 0.16666666666666669,    0.5000000000000001};
+// {2/pi, -pi/2 head, -pi/2 middle, -pi/2 tail (sign folded), log2(e), -ln2 head, -ln2 tail, rint magic}
+__constant__ double kRed[8] = {0.6366197723675814,  -1.5707963267948966,  -6.123233995736766e-17,  1.4973849048591698e-33,
+                               1.4426950408889634,  -0.6931471805599453,  -2.3190468138462996e-17, 6755399441055744.0};
 
 __device__ __forceinline__ double rcp_seed(double d) {
     double y;
@@ -30,13 +43,11 @@ __device__ __forceinline__ double rcp_seed(double d) {
 
 // 1/d for finite normal d (any sign), error < 1 ulp (correctly rounded in all but rare cases)
 __device__ __forceinline__ double recip(double d) {
-    double y = rcp_seed(d);
+    double y = rcp_seed(d); // ~2^-23 relative
     double e = fma(-d, y, 1.0);
-    y = fma(y, e, y);
+    y = fma(y, e, y);       // ~2^-46
     e = fma(-d, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-d, y, 1.0);
-    y = fma(y, e, y);
+    y = fma(y, e, y);       // rounding-limited
     return y;
 }
 
@@ -49,25 +60,25 @@ __device__ __forceinline__ double div_by(double n, double d, double rc) {
 
 // sin and cos of x, |x| <= kTrigFastMax (NaN in -> NaN out)
 __device__ __forceinline__ void sincos_fast(double x, double& s, double& c) {
-    const double kMagic = 6755399441055744.0; // 1.5 * 2^52: rint() by addition
-    const double q = fma(x, 0.6366197723675814, kMagic);
+    const double magic = kRed[7]; // 1.5 * 2^52: rint() by addition
+    const double q = fma(x, kRed[0], magic);
     const int n = __double2loint(q);
-    const double j = q - kMagic;
-    double r = fma(j, -1.5707963267948966, x);
-    r = fma(j, -6.123233995736766e-17, r);
-    r = fma(j, 1.4973849048591698e-33, r);
+    const double j = q - magic;
+    double r = fma(j, kRed[1], x);
+    r = fma(j, kRed[2], r);
+    r = fma(j, kRed[3], r);
     const double z = r * r;
     // fdlibm __kernel_sin / __kernel_cos minimax coefficients on [-pi/4, pi/4]
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(ps, z, 2.75573137070700676789e-06);
-    ps = fma(ps, z, -1.98412698298579493134e-04);
-    ps = fma(ps, z, 8.33333333332248946124e-03);
-    ps = fma(ps, z, -1.66666666666666324348e-01);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(pc, z, -2.75573143513906633035e-07);
-    pc = fma(pc, z, 2.48015872894767294178e-05);
-    pc = fma(pc, z, -1.38888888888741095749e-03);
-    pc = fma(pc, z, 4.16666666666666019037e-02);
+    double ps = fma(z, kSinC[0], kSinC[1]);
+    ps = fma(ps, z, kSinC[2]);
+    ps = fma(ps, z, kSinC[3]);
+    ps = fma(ps, z, kSinC[4]);
+    ps = fma(ps, z, kSinC[5]);
+    double pc = fma(z, kCosC[0], kCosC[1]);
+    pc = fma(pc, z, kCosC[2]);
+    pc = fma(pc, z, kCosC[3]);
+    pc = fma(pc, z, kCosC[4]);
+    pc = fma(pc, z, kCosC[5]);
     const double sn = fma(ps, r * z, r);
     const double cs = fma(z * z, pc, fma(z, -0.5, 1.0));
     // x = j pi/2 + r : quadrant n mod 4
@@ -80,31 +91,25 @@ __device__ __forceinline__ void sincos_fast(double x, double& s, double& c) {
     c = __hiloint2double(chi, __double2loint(cc));
 }
 
-// exp(x) for any x (NaN -> NaN, large -> +inf, very negative -> 0)
+// exp(x) for any non-NaN x (large -> +inf, very negative -> 0); NaN is treated as -760 by the
+// clamp, which is harmless here: a NaN can only come from a drone whose state is already NaN.
 __device__ __forceinline__ double exp_fast(double x) {
-    const double kMagic = 6755399441055744.0;
+    const double magic = kRed[7];
     // clamp so that k stays within the two-step scaling range; exp is saturated out there anyway
     const double xc = fmin(fmax(x, -760.0), 760.0);
-    const double q = fma(xc, 1.4426950408889634, kMagic);
+    const double q = fma(xc, kRed[4], magic);
     const int k = __double2loint(q);
-    const double j = q - kMagic;
-    double r = fma(j, -0.6931471805599453, xc);
-    r = fma(j, -2.3190468138462996e-17, r);
-    double g = fma(r, 2.5100424157005067e-08, 2.7620138719733994e-07);
-    g = fma(g, r, 2.7557268378684192e-06);
-    g = fma(g, r, 2.480152119021773e-05);
-    g = fma(g, r, 0.00019841269863105968);
-    g = fma(g, r, 0.0013888888917281794);
-    g = fma(g, r, 0.008333333333330051);
-    g = fma(g, r, 0.04166666666662399);
-    g = fma(g, r, 0.16666666666666669);
-    g = fma(g, r, 0.5000000000000001);
+    const double j = q - magic;
+    double r = fma(j, kRed[5], xc);
+    r = fma(j, kRed[6], r);
+    double g = fma(r, kExpC[0], kExpC[1]);
+#pragma unroll
+    for (int i = 2; i < 10; ++i) g = fma(g, r, kExpC[i]);
     const double e = fma(r * r, g, r) + 1.0;
     const int k1 = k >> 1, k2 = k - k1; // |k| <= 1097 => both halves are normal powers of two
     const double s1 = __hiloint2double((k1 + 1023) << 20, 0);
     const double s2 = __hiloint2double((k2 + 1023) << 20, 0);
-    const double y = (e * s1) * s2;
-    return x != x ? x : y; // fmin/fmax swallowed a NaN
+    return (e * s1) * s2;
 }
 
 // brain.py:37-39 : 1 / (exp(-beta x) + 1)

@@ -45,34 +45,35 @@ struct Drone {
 };
 
 // geometry.py:26-40 (sin/cos of the three angles) and :62-69 (Tr entries, float32)
-__device__ __forceinline__ void trig_update(Drone& d) {
-    Trig& g = d.trig;
-    const double roll = d.x[3], pitch = d.x[4], yaw = d.x[5];
-    sincos_fast(roll, g.sr, g.cr);
-    sincos_fast(pitch, g.sp, g.cp);
-    sincos_fast(yaw, g.sy, g.cy);
-    double tp;
-    // |angle| beyond the fast reduction's range (never seen in practice: angles are unwrapped but
-    // episodes end long before): CUDA libm with Payne-Hanek reduction, warp-uniform branch
-    const bool big = !(fabs(roll) <= kTrigFastMax && fabs(pitch) <= kTrigFastMax && fabs(yaw) <= kTrigFastMax);
-    if (__any_sync(0xffffffffu, big)) {
-        if (big) {
-            sincos(roll, &g.sr, &g.cr);
-            sincos(pitch, &g.sp, &g.cp);
-            sincos(yaw, &g.sy, &g.cy);
-        }
-    }
-    const double rc = recip(g.cp);
-    tp = div_by(g.sp, g.cp, rc); // np.tan(pitch) to ~2 ulp
-    if (__any_sync(0xffffffffu, big)) {
-        if (big) tp = tan(pitch);
-    }
+__device__ __forceinline__ void trig_finish(Trig& g, double tp, double rc) {
     g.t01 = __double2float_rn(g.sr * tp);
     g.t02 = __double2float_rn(g.cr * tp);
     g.t11 = __double2float_rn(g.cr);
     g.t12 = __double2float_rn(-g.sr);
     g.t21 = __double2float_rn(div_by(g.sr, g.cp, rc));
     g.t22 = __double2float_rn(div_by(g.cr, g.cp, rc));
+}
+
+__device__ __forceinline__ void trig_update(Drone& d) {
+    Trig& g = d.trig;
+    const double roll = d.x[3], pitch = d.x[4], yaw = d.x[5];
+    sincos_fast(roll, g.sr, g.cr);
+    sincos_fast(pitch, g.sp, g.cp);
+    sincos_fast(yaw, g.sy, g.cy);
+    const double rc = recip(g.cp);
+    trig_finish(g, div_by(g.sp, g.cp, rc), rc); // np.tan(pitch) = sin/cos to ~2 ulp
+    // |angle| beyond the fast reduction's range (never seen in practice: angles are unwrapped but
+    // episodes end long before): redo everything with CUDA's libm (Payne-Hanek reduction).
+    // One warp-uniform, normally-not-taken branch after the straight-line code.
+    const bool big = !(fabs(roll) <= kTrigFastMax && fabs(pitch) <= kTrigFastMax && fabs(yaw) <= kTrigFastMax);
+    if (__any_sync(0xffffffffu, big)) {
+        if (big) {
+            sincos(roll, &g.sr, &g.cr);
+            sincos(pitch, &g.sp, &g.cp);
+            sincos(yaw, &g.sy, &g.cy);
+            trig_finish(g, tan(pitch), recip(g.cp));
+        }
+    }
 }
 
 __device__ __forceinline__ void drone_reset(const ld_params& p, Drone& d) {

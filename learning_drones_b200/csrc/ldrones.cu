@@ -341,29 +341,34 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             }
             continue;
         }
-        // ---- one timestep of flight/__init__.py:39-93 ------------------------------------------
+        // ---- hot loop: timesteps of flight/__init__.py:39-93 until some lane's episode ends ---------
+        // `live` cannot change inside: lanes only leave (publish) or join (refill) outside of it.
         const bool live = idx >= 0;
         double a_last[6];
-        int u;
-        step_rewards_and_coin(p, d, live, time_reward);
-        const bool crashed = physics_step<EXTRAS>(p, d, rcp_m, MODE != kPlain ? a_last : nullptr, u) && live;
-        d.reward += crashed ? p.reward_crashed : ((live ? u : 0) * p.reward_unstable);
-        d.unstable += (live && !crashed) ? u : 0;
-        d.status |= crashed ? LD_STATUS_CRASHED : 0;
-        if (MODE == kTrace) {
-            if (live) write_state(d, a_last, trace + (size_t)t * LD_STATE_LEN);
-        }
-        // next step's trigonometry and this step's brain: independent, interleaved by the scheduler
-        trig_update(d);
-        brain(d, taddr, wrow, neg_beta, MODE != kPlain && crashed);
-        if (MODE == kTrace) {
-            if (live && !crashed) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) trace[(size_t)t * LD_STATE_LEN + 24 + i] = d.thrust[i];
+        bool crashed, done;
+        do {
+            int u;
+            step_rewards_and_coin(p, d, live, time_reward);
+            crashed = physics_step<EXTRAS>(p, d, rcp_m, MODE != kPlain ? a_last : nullptr, u) && live;
+            d.reward += crashed ? p.reward_crashed : ((live ? u : 0) * p.reward_unstable);
+            d.unstable += (live && !crashed) ? u : 0;
+            d.status |= crashed ? LD_STATUS_CRASHED : 0;
+            if (MODE == kTrace) {
+                if (live) write_state(d, a_last, trace + (size_t)t * LD_STATE_LEN);
             }
-        }
-        t += live ? 1 : 0;
-        if (live && (crashed || t >= H)) {
+            // next step's trigonometry and this step's brain: independent, interleaved by the scheduler
+            trig_update(d);
+            brain(d, taddr, wrow, neg_beta, MODE != kPlain && crashed);
+            if (MODE == kTrace) {
+                if (live && !crashed) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) trace[(size_t)t * LD_STATE_LEN + 24 + i] = d.thrust[i];
+                }
+            }
+            t += live ? 1 : 0;
+            done = live && (crashed || t >= H);
+        } while (!__any_sync(0xffffffffu, done));
+        if (done) {
             publish<MODE>(p, d, a_last, idx, records, final_state);
             idx = -1;
         }
