@@ -170,6 +170,10 @@ int ld_reduce_records_device(const ld_record* records, int64_t n, int64_t* stats
  * as DFMA per max-clock cycle per SM. */
 int ld_measure_fp64_peak(double* tflops_out, double* dfma_per_clk_per_sm_out);
 
+/* Accuracy tap for the kernel's own elementary functions (csrc/ld_math.cuh); device pointers.
+ * fn 0: out0=sin(x) out1=cos(x) | 1: out0=exp(x) | 2: out0=1/(exp(-0.4x)+1) | 3: out0=x/y out1=1/y */
+int ld_debug_math_device(int fn, const double* x, const double* y, double* out0, double* out1, int64_t n, void* stream);
+
 /* frees the device workspace that ld_fly_mlp_f64_host keeps between calls (per host thread) */
 void ld_release_workspace(void);
 

@@ -22,6 +22,7 @@ EXPORTS = (
     "ld_reduce_records_device",
     "ld_release_workspace",
     "ld_measure_fp64_peak",
+    "ld_debug_math_device",
 )
 
 
@@ -63,6 +64,8 @@ def load():
     L.ld_release_workspace.restype = None
     L.ld_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ld_measure_fp64_peak.restype = C.c_int
+    L.ld_debug_math_device.argtypes = [C.c_int, vp, vp, vp, vp, i64, vp]
+    L.ld_debug_math_device.restype = C.c_int
     if L.ld_abi_version() != LD_ABI_VERSION:
         raise ImportError(f"libldrones ABI {L.ld_abi_version()} != python binding {LD_ABI_VERSION}; rebuild")
     _lib = L

@@ -380,6 +380,27 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
 }
 
+// ---- accuracy tap for ld_math.cuh (tests/test_gpu_math.py) --------------------------------------
+__global__ void debug_math_kernel(int fn, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ o0,
+                                  double* __restrict__ o1, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (fn == 0) {
+            double s, c;
+            sincos_fast(x[i], s, c);
+            o0[i] = s;
+            o1[i] = c;
+        } else if (fn == 1) {
+            o0[i] = exp_fast(x[i]);
+        } else if (fn == 2) {
+            o0[i] = sigmoid_fast(x[i], -0.4);
+        } else if (fn == 3) {
+            const double rc = recip(y[i]);
+            o0[i] = div_by(x[i], y[i], rc);
+            o1[i] = rc;
+        }
+    }
+}
+
 // ---- population statistics: warp-shuffle reductions -----------------------------------------
 __device__ __forceinline__ unsigned long long pack_key(long long reward, long long i) {
     long long r = reward < -2147483648LL ? -2147483648LL : (reward > 2147483647LL ? 2147483647LL : reward);
@@ -627,20 +648,16 @@ int ld_fly_mlp_f64_host(const ld_params* params, const double* genomes, int64_t 
     if (!genomes || !records) return fail(LD_ERR_INVALID_ARG, "NULL host buffer");
     rc = ensure_device();
     if (rc) return rc;
-    // chunk = whole waves so every chunk fills the machine; two buffers so the H2D copy of chunk
-    // i+1 and the D2H copy of chunk i-1 overlap the kernel of chunk i
+    // Chunks are whole waves (every chunk fills the machine) and ramp up 1, 2, 4, 4, ... waves: only
+    // the first, smallest H2D copy is exposed; later copies and the D2H of finished chunks overlap
+    // the kernel of the chunk in between (two buffers, two streams).
     const int64_t wave = (int64_t)g_dev.sms * kCtaThreads;
-    int64_t chunk = n;
-    if (n > 2 * wave) {
-        int64_t waves = (n + wave - 1) / wave;
-        int64_t per = waves >= 8 ? (waves + 3) / 4 : (waves + 1) / 2;
-        if (per > 8) per = 8;
-        chunk = per * wave;
-    }
-    rc = ws_reserve((size_t)chunk, final_state != nullptr);
+    const int64_t max_chunk = (n < 4 * wave) ? (n < wave ? n : (n + wave - 1) / wave * wave) : 4 * wave;
+    rc = ws_reserve((size_t)(max_chunk < n ? max_chunk : n), final_state != nullptr);
     if (rc) return rc;
     int b = 0;
-    for (int64_t off = 0; off < n; off += chunk, b ^= 1) {
+    int64_t chunk = wave;
+    for (int64_t off = 0; off < n; b ^= 1) {
         const int64_t m = (n - off < chunk) ? (n - off) : chunk;
         cudaStream_t s = g_ws.streams[b];
         LD_CUDA(cudaMemcpyAsync(g_ws.genomes[b], genomes + off * LD_GENOME_LEN, (size_t)m * LD_GENOME_LEN * sizeof(double),
@@ -652,6 +669,8 @@ int ld_fly_mlp_f64_host(const ld_params* params, const double* genomes, int64_t 
         if (final_state)
             LD_CUDA(cudaMemcpyAsync(final_state + off * LD_STATE_LEN, g_ws.state[b], (size_t)m * LD_STATE_LEN * sizeof(double),
                                     cudaMemcpyDeviceToHost, s));
+        off += m;
+        if (chunk < 4 * wave) chunk *= 2;
     }
     LD_CUDA(cudaStreamSynchronize(g_ws.streams[0]));
     LD_CUDA(cudaStreamSynchronize(g_ws.streams[1]));
@@ -677,6 +696,14 @@ int ld_reduce_records_device(const ld_record* records, int64_t n, int64_t* stats
 }
 
 void ld_release_workspace(void) { ws_release(); }
+
+int ld_debug_math_device(int fn, const double* x, const double* y, double* out0, double* out1, int64_t n, void* stream) {
+    if (fn < 0 || fn > 3 || n < 0 || (n > 0 && (!x || !out0))) return fail(LD_ERR_INVALID_ARG, "bad arguments");
+    if (n == 0) return LD_OK;
+    debug_math_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(fn, x, y ? y : x, out0, out1 ? out1 : out0, n);
+    LD_CUDA(cudaGetLastError());
+    return LD_OK;
+}
 
 int ld_measure_fp64_peak(double* tflops_out, double* dfma_per_clk_per_sm_out) {
     if (!tflops_out) return fail(LD_ERR_INVALID_ARG, "NULL output");
