@@ -52,43 +52,67 @@ def population(kind, n, seed=2026):
 
 
 class ClockSampler:
-    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock / throttle-reason sampler running DURING the timed region (NVML, every ~5 ms;
+    falls back to `nvidia-smi -lms 20`)."""
 
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop_flag, self.thread, self.max_mhz = index, [], False, None, None
+
+    def _loop_nvml(self):
+        import pynvml as N
+
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.rows.append((time.perf_counter(), float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)),
+                                  N.nvmlDeviceGetPowerUsage(h) / 1000.0, int(get_reasons(h))))
+            except N.NVMLError:
+                pass
+            time.sleep(0.005)
+
+    def _loop_smi(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active"
+        proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "20"],
+                                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        for line in proc.stdout:
+            if self.stop_flag:
+                break
+            f = [x.strip() for x in line.split(",")]
+            try:
+                self.max_mhz = float(f[1])
+                self.rows.append((time.perf_counter(), float(f[0]), float(f[2]), int(f[3], 16)))
+            except (ValueError, IndexError):
+                pass
+        proc.terminate()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml  # noqa: F401
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+            target = self._loop_nvml
+        except ImportError:
+            target = self._loop_smi
+        self.thread = threading.Thread(target=target, daemon=True)
+        self.thread.start()
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return None
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.2] or [r for _, r in self.rows]
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
         if not rows:
             return None
-        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
-        reasons = []
-        for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
-            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in rows):
-                reasons.append(name)
-        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][1]) if rows[0][1].isdigit() else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
+        sm = sorted(r[1] for r in rows)
+        mask = 0
+        for r in rows:
+            mask |= r[3]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "power_w_max": max(r[2] for r in rows),
+                "samples": len(rows), "reasons": [name for bit, name in self.REASONS if mask & bit]}
 
 
 def measured_peaks():
@@ -150,7 +174,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--population", default="survivors", choices=["survivors", "random"])
@@ -173,6 +197,7 @@ def main():
 
     from learning_drones_b200 import _lib, population as ldpop
     from learning_drones_b200._abi import RECORD_DTYPE, make_params
+    from learning_drones_b200.distributed import allgather_records
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -189,12 +214,12 @@ def main():
     genomes = pinned.to(dev)
     records = torch.empty((D, 4), dtype=torch.int64, device=dev)
     counter = torch.empty(1, dtype=torch.int64, device=dev)
-    gathered = torch.empty((world * D, 4), dtype=torch.int64, device=dev) if world > 1 else None
 
     def step():
         ldpop.fly_population_device(genomes, params, records=records, work_counter=counter)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, records)  # fitness allgather for selection (NCCL/NVLink)
+            return allgather_records(records, n_global=D * world)  # fitness all-gather for selection (NCCL/NVLink)
+        return records
 
     def barrier():
         if world > 1:
@@ -209,7 +234,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.05)
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -220,7 +245,7 @@ def main():
         ldpop.fly_population_device(genomes, params, records=records, work_counter=counter)
         b.record()
         if world > 1:
-            dist.all_gather_into_tensor(gathered, records)
+            allgather_records(records, n_global=D * world)
     e_all1.record()
     barrier()
     t_wall1 = time.perf_counter()
