@@ -1,0 +1,172 @@
+"""CPU tests of the host side: C-ABI surface, ld_params derivation, reference-API mirror.
+
+Where the reference tree is available (build container) the mirror classes are compared with
+the reference's own classes under identical seeds; on the GPU box those tests skip."""
+import contextlib
+import ctypes as C
+import io
+import math
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+from learning_drones_b200 import _abi, _lib
+from learning_drones_b200._abi import GENOME_LEN, LAYER_SHAPES, LdParams, LdRecord, make_params, sqrt_threshold
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+needs_ref = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "evolve")), reason="reference tree not present")
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "ldrones.h")).read()
+    declared = set(re.findall(r"^(?:int|int64_t|void|const char\*)\s+(ld_[a-z0-9_]+)\s*\(", hdr, re.M))
+    L = _lib.load()  # loads without a GPU; raises if the .so is missing
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.ld_abi_version() == _abi.LD_ABI_VERSION
+
+
+def test_struct_layout_matches_header():
+    # sizes implied by include/ldrones.h (doubles 8-aligned, explicit pads)
+    assert C.sizeof(LdRecord) == 32
+    assert C.sizeof(LdParams) % 8 == 0
+    p = make_params()
+    assert LdParams.dt.offset == 8 * 10 + 4 * 8  # 10 doubles, then 2+3+3 floats
+    assert p.timesteps == 2500 and p.reward_time == 1 and p.punish_time == 0
+
+
+def test_params_follow_reference_constants():
+    p = make_params(2000)
+    G = 9.81 * (4 * 0.050 + 0.200)
+    assert p.neg_G32 == np.float32(-G) and p.m_total32 == np.float32(0.2 + 4 * 0.05 + 0)
+    assert p.sqrt2_r_m == float(np.sqrt(2) * 0.1)
+    assert list(p.inv_I) == [1 / 2160e-6, 1 / 2160e-6, 1 / 4210e-6]
+    assert list(p.wind_cw32) == [0.0, 0.0, 0.0] and list(p.moments_payload) == [0.0, 0.0, 0.0]
+    assert list(p.init_pos) == [0.0, 0.0, 10.0] and list(p.init_thrust) == [0.0] * 4
+    assert (p.reward_time_passed, p.reward_crashed, p.reward_unstable, p.reward_coin_distance) == (2, -3000, -1, -100)
+    assert p.angle_limit == np.pi / 4 and p.angle_vel_limit == 20 and (p.z_min, p.z_max) == (0.0, 80.0)
+    assert list(p.coin0_pos) == [5.0, 5.0, 10.0] and list(p.coin_step) == [5.0, 2.5, 0.0]
+    assert (p.coin0_value, p.coinN_value, p.coin0_radius, p.coinN_radius) == (2000, 1000, 2.0, 1.0)
+    w = make_params(10, wind_speed=[0.5, -2.0, 0.25], mass_payload=0.05, x_payload=0.01, y_payload=-0.02)
+    assert list(w.wind_cw32) == [float(np.float32(v) * np.float32(0.1)) for v in (0.5, -2.0, 0.25)]
+    assert w.neg_G32 == np.float32(-(G + 9.81 * 0.05))
+    with pytest.raises(ValueError):
+        make_params(-1)
+
+
+@pytest.mark.parametrize("r", [1.0, 2.0, 1.25, 1.5, 0.1, 3.3, 1e-3, 7.0])
+def test_sqrt_threshold_is_exact(r):
+    thr = sqrt_threshold(r)
+    below = math.nextafter(thr, 0.0)
+    assert math.sqrt(thr) >= r and math.sqrt(below) < r
+    # the reference's test `norm < radius` and the kernel's `norm^2 < thr` agree around the boundary
+    for s in (below, thr, math.nextafter(thr, math.inf), r * r):
+        assert (math.sqrt(s) < r) == (s < thr)
+    assert sqrt_threshold(1.0) == 1.0 and sqrt_threshold(2.0) == 4.0
+
+
+def test_genome_roundtrip_and_flatten_order():
+    from learning_drones_b200.evolve.brain import NeuralNetwork
+
+    np.random.seed(3)
+    nn = NeuralNetwork(layer_spec={1: 10, 2: 10, 3: 4})
+    assert tuple(w.shape for w in nn.weights) == LAYER_SHAPES
+    g = nn.genome()
+    assert g.shape == (GENOME_LEN,)
+    # layer.flatten() order of evolve/util.py:58-59, bias last column
+    assert g[15] == nn.weights[0][0, 15] and g[16] == nn.weights[0][1, 0] and g[160 + 10] == nn.weights[1][0, 10]
+    assert g[270 + 11 * 3 + 10] == nn.weights[2][3, 10]
+    nn2 = NeuralNetwork(layer_spec={1: 10, 2: 10, 3: 4})
+    nn2.set_genome(g)
+    assert all(np.array_equal(a, b) for a, b in zip(nn.weights, nn2.weights))
+    with pytest.raises(ValueError):
+        NeuralNetwork().genome()  # default 15-8-10-4 shape is not the Drone's
+
+
+def test_drone_reset_and_guards():
+    from learning_drones_b200.drone.drone import Drone
+
+    d = Drone(visualize=False, n_servers=0)
+    assert d.position.shape == (3, 1) and d.thrust.shape == (4, 1) and d.distance_to_coin == np.inf
+    assert len(d.sensors) == 6 and d.sensors[2].previous_pos == 10.0
+    d.reward, d.flight_time = 5, 3
+    with pytest.raises(RuntimeError):
+        d.start_state()
+    d.reset()
+    assert d.reward == 0 and d.flight_time == 0 and not d.crashed
+    with pytest.raises(NotImplementedError):
+        Drone(visualize=True, n_servers=1)
+
+
+def _ref_modules():
+    np.Infinity = np.inf
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import logging
+
+    logging.disable(logging.CRITICAL)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import drone.drone as rdrone
+        import evolve.brain as rbrain
+        import evolve.util as rutil
+    return rdrone, rbrain, rutil
+
+
+@needs_ref
+def test_mirror_classes_match_reference_under_same_seed(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)  # reference Drone() creates ./evolution/<timestamp>/
+    rdrone, rbrain, rutil = _ref_modules()
+    from learning_drones_b200.drone.drone import Drone
+    from learning_drones_b200.evolve import util
+    from learning_drones_b200.evolve.brain import NeuralNetwork
+
+    # brain init: same draws from the global numpy stream
+    np.random.seed(11)
+    a = rbrain.NeuralNetwork(layer_spec={1: 10, 2: 10, 3: 4})
+    np.random.seed(11)
+    b = NeuralNetwork(layer_spec={1: 10, 2: 10, 3: 4})
+    assert all(np.array_equal(x, y) for x, y in zip(a.weights, b.weights))
+    x = np.random.standard_normal((15, 1))
+    assert np.array_equal(a.feed_forward(x), b.feed_forward(x))
+
+    def population(cls, seed, n=8):
+        np.random.seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ds = [cls(visualize=False, n_servers=0) for _ in range(n)]
+        for i, d in enumerate(ds):
+            d.reward = int((i * 7919) % 13) - 5
+        return ds
+
+    ref_pop, our_pop = population(rdrone.Drone, 5), population(Drone, 5)
+    assert all(np.array_equal(x, y) for r, o in zip(ref_pop, our_pop) for x, y in zip(r.controller.weights, o.controller.weights))
+    # selection + crossover + mutate: identical RNG consumption and identical children
+    np.random.seed(77)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref_new = rutil.selection_and_crossover(ref_pop, 0.6, 0.5)
+    for d in ref_new:
+        d.mutate(0.05)
+    ref_state = np.random.random_sample()
+    np.random.seed(77)
+    our_new = util.selection_and_crossover(our_pop, 0.6, 0.5)
+    for d in our_new:
+        d.mutate(0.05)
+    assert np.random.random_sample() == ref_state
+    for r, o in zip(ref_new, our_new):
+        assert all(np.array_equal(x, y) for x, y in zip(r.controller.weights, o.controller.weights))
+    assert util.get_best_of_generation([3, 9, 9, -1]) == rutil.get_best_of_generation([3, 9, 9, -1]) == (1, 9)
+    util.compare_weights(our_new[0], our_new[0])
+    with pytest.raises(AssertionError):
+        util.compare_weights(our_new[0], our_new[1])
+
+
+def test_bench_population_matches_fixture_generators(golden):
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert np.array_equal(bench.population("survivors", 65536)[:96], golden("survivors_2000")["genomes"])
+    assert np.array_equal(bench.population("random", 65536)[:512], golden("random_2000")["genomes"])
