@@ -64,6 +64,7 @@ typedef enum ld_status {
 /* status bits of ld_record.status */
 #define LD_STATUS_CRASHED 1   /* drone/drone.py:150-154 */
 #define LD_STATUS_NONFINITE 2 /* z became NaN: reference would raise in int(nan), drone.py:14 */
+#define LD_STATUS_FINISHED 4  /* PID mode: every target coin collected (collect_coins.py:289-292) */
 
 /*
  * Everything fly() reads that is not the brain.  Derived constants are
@@ -158,6 +159,33 @@ int ld_fly_mlp_f64_host(const ld_params* params, const double* genomes, int64_t 
  * step are left untouched. Device pointers. */
 int ld_fly_mlp_f64_trace_device(const ld_params* params, const double* genome,
                                 ld_record* record, double* trace, void* stream);
+
+/* ---- PID-controlled episode (second controller mode) ------------
+ * The main loop of flight/collect_coins.py:278-364 for a batch of PID gain sets: per step
+ * score-1, coin test on the current target (+value, next target), exit when all targets are
+ * collected, physics + integrator (same as the MLP mode, no crash rule), cascaded PIDs
+ * (drone/controller/pid.py:77-106,132-142 "signChange"; drone/onboard_computer.py:50-118). */
+typedef struct ld_pid_params {
+    int32_t n_coins;   /* 4 */
+    int32_t timesteps; /* 3500; the score starts at this value (collect_coins.py:276-277) */
+    int32_t step_reward; /* -1 */
+    int32_t _pad;
+    double coin_pos[LD_PID_MAX_COINS][3]; /* collect_coins.py:253-258 */
+    double coin_thr2[LD_PID_MAX_COINS];   /* sqrt-threshold of each radius (see ld_params.coin0_thr2) */
+    int32_t coin_value[LD_PID_MAX_COINS];
+    double integral_range;        /* 2 */
+    double out_lo[6], out_hi[6];  /* output limits of the x y z roll pitch yaw PIDs (collect_coins.py:125-188) */
+    double base_thrust;           /* G / (4 c_f)  onboard_computer.py:97 */
+    double yaw_setpoint;          /* 0 */
+} ld_pid_params;
+
+/* pid_gains [n][6][3]: (kp, ki, kd) of the x, y, z, roll, pitch, yaw controllers of every drone.
+ * records: reward = final score, coins, flight_time = loop iterations entered, status
+ * (LD_STATUS_FINISHED), distance_to_coin = distance to the current target.  Device pointers. */
+int ld_fly_pid_f64_device(const ld_params* params, const ld_pid_params* pid, const double* pid_gains, int64_t n,
+                          ld_record* records, double* final_state, void* stream);
+int ld_fly_pid_f64_host(const ld_params* params, const ld_pid_params* pid, const double* pid_gains, int64_t n,
+                        ld_record* records, double* final_state);
 
 /* ---- population statistics (warp-shuffle reductions) ----------------------
  * stats[0]=sum flight_time (active drone-steps), [1]=max reward, [2]=argmax reward

@@ -21,6 +21,8 @@ PID_GAINS = 18
 
 STATUS_CRASHED = 1
 STATUS_NONFINITE = 2
+STATUS_FINISHED = 4
+PID_MAX_COINS = 8
 
 # drone/drone.py:10-17 of the reference
 DELTA_T = 0.01
@@ -192,3 +194,59 @@ def make_params(
     p.reward_time = int(bool(reward_time))
     p.punish_time = int(bool(punish_time))
     return p
+
+
+class LdPidParams(C.Structure):
+    _fields_ = [
+        ("n_coins", C.c_int32),
+        ("timesteps", C.c_int32),
+        ("step_reward", C.c_int32),
+        ("_pad", C.c_int32),
+        ("coin_pos", (C.c_double * 3) * PID_MAX_COINS),
+        ("coin_thr2", C.c_double * PID_MAX_COINS),
+        ("coin_value", C.c_int32 * PID_MAX_COINS),
+        ("integral_range", C.c_double),
+        ("out_lo", C.c_double * 6),
+        ("out_hi", C.c_double * 6),
+        ("base_thrust", C.c_double),
+        ("yaw_setpoint", C.c_double),
+    ]
+
+
+# flight/collect_coins.py:253-258
+PID_TARGET_COINS = ((0.0, 0.0, 5.0), (25.0, 25.0, 5.0), (-10.0, 35.0, 5.0), (0.0, 0.0, 5.0))
+
+
+def make_pid_params(timesteps: int = 3500, coins=PID_TARGET_COINS, coin_radius=1, coin_value=1000,
+                    gravity=P.gravity, mass_motor=P.mass_motor, mass_center=P.mass_center, coef_force=P.coef_force) -> LdPidParams:
+    """Episode constants of the reference's flight/collect_coins.py main loop (:125-188, :253-277)."""
+    coins = [tuple(float(v) for v in c) for c in coins]
+    if not 1 <= len(coins) <= PID_MAX_COINS:
+        raise ValueError(f"1..{PID_MAX_COINS} target coins")
+    q = LdPidParams()
+    q.n_coins, q.timesteps, q.step_reward = len(coins), int(timesteps), -1
+    for i, c in enumerate(coins):
+        q.coin_pos[i][:] = c
+        q.coin_thr2[i] = sqrt_threshold(coin_radius)
+        q.coin_value[i] = int(coin_value)
+    q.integral_range = 2.0
+    lim4, lim6 = float(np.pi / 4), float(np.pi / 6)
+    #            x      y      z    roll   pitch  yaw     (collect_coins.py:125-188; z keeps PID's default [-1, 1])
+    q.out_lo[:] = [-lim4, -lim4, -1.0, -lim4, -lim4, -lim6]
+    q.out_hi[:] = [lim4, lim4, 1.0, lim4, lim4, lim6]
+    G = gravity * (4 * mass_motor + mass_center)
+    q.base_thrust = float(G / (4 * coef_force))  # onboard_computer.py:97
+    q.yaw_setpoint = 0.0
+    return q
+
+
+def paramset_to_pid_gains(paramset18) -> np.ndarray:
+    """(.., 18) gains in choose_paramset.convert_paramset_2_float order -> (.., 6, 3) per-controller
+    (kp, ki, kd) for x, y, z, roll, pitch, yaw, wired like collect_coins.py:125-188 — including
+    its use of ki_y for the z controller (:181)."""
+    g = np.asarray(paramset18, dtype=np.float64)
+    if g.shape[-1] != PID_GAINS:
+        raise ValueError(f"expected {PID_GAINS} gains, got {g.shape}")
+    kp_x, kp_y, kp_z, ki_x, ki_y, ki_z, kd_x, kd_y, kd_z, kp_r, kp_p, kp_w, ki_r, ki_p, ki_w, kd_r, kd_p, kd_w = np.moveaxis(g, -1, 0)
+    rows = [(kp_x, ki_x, kd_x), (kp_y, ki_y, kd_y), (kp_z, ki_y, kd_z), (kp_r, ki_r, kd_r), (kp_p, ki_p, kd_p), (kp_w, ki_w, kd_w)]
+    return np.ascontiguousarray(np.stack([np.stack(r, axis=-1) for r in rows], axis=-2))

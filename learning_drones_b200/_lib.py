@@ -5,7 +5,7 @@ There is NO fallback: if the shared library is missing or a call fails, this rai
 import ctypes as C
 import os
 
-from ._abi import LD_ABI_VERSION, LdParams, LdRecord
+from ._abi import LD_ABI_VERSION, LdParams, LdPidParams, LdRecord
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libldrones.so")
@@ -23,6 +23,8 @@ EXPORTS = (
     "ld_release_workspace",
     "ld_measure_fp64_peak",
     "ld_debug_math_device",
+    "ld_fly_pid_f64_device",
+    "ld_fly_pid_f64_host",
 )
 
 
@@ -66,6 +68,10 @@ def load():
     L.ld_measure_fp64_peak.restype = C.c_int
     L.ld_debug_math_device.argtypes = [C.c_int, vp, vp, vp, vp, i64, vp]
     L.ld_debug_math_device.restype = C.c_int
+    L.ld_fly_pid_f64_device.argtypes = [C.POINTER(LdParams), C.POINTER(LdPidParams), dp, i64, vp, dp, vp]
+    L.ld_fly_pid_f64_device.restype = C.c_int
+    L.ld_fly_pid_f64_host.argtypes = [C.POINTER(LdParams), C.POINTER(LdPidParams), dp, i64, vp, dp]
+    L.ld_fly_pid_f64_host.restype = C.c_int
     if L.ld_abi_version() != LD_ABI_VERSION:
         raise ImportError(f"libldrones ABI {L.ld_abi_version()} != python binding {LD_ABI_VERSION}; rebuild")
     _lib = L

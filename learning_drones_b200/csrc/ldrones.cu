@@ -380,6 +380,120 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
 }
 
+// ---- PID controller mode: flight/collect_coins.py:278-364 for a batch of gain sets ---------------
+struct PidCtl {
+    double kp, ki, kd, I, prev_e, prev_pv;
+};
+
+// drone/controller/pid.py:77-106 ("signChange"), :132-134 (accumulate), :136-142 (clamp)
+__device__ __forceinline__ double pid_calculate(PidCtl& c, double set, double pv, double dt, double rc_dt, double range,
+                                                double lo, double hi) {
+    const double error = set - pv;
+    if (c.prev_e * error < 0.0) c.I = 0.0;
+    if (fabs(error) < range) c.I = c.I + error;
+    const double diff = (c.prev_pv != 0.0) ? pv - c.prev_pv : 0.0;
+    double out = c.kp * error + c.ki * c.I * dt - div_by(c.kd * diff, dt, rc_dt);
+    c.prev_pv = pv;
+    if (error != 0.0) c.prev_e = error;
+    out = out < lo ? lo : (out > hi ? hi : out);
+    return out;
+}
+
+template <bool EXTRAS>
+__global__ void __launch_bounds__(128)
+fly_pid_f64_kernel(const __grid_constant__ ld_params p, const __grid_constant__ ld_pid_params q,
+                   const double* __restrict__ gains, long long n, ld_record* __restrict__ records,
+                   double* __restrict__ final_state) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool exists = i < n;
+    const double* __restrict__ g = gains + (exists ? i : 0) * 18;
+    PidCtl pid[6]; // x y z roll pitch yaw
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        pid[k].kp = __ldg(g + 3 * k);
+        pid[k].ki = __ldg(g + 3 * k + 1);
+        pid[k].kd = __ldg(g + 3 * k + 2);
+        pid[k].I = pid[k].prev_e = pid[k].prev_pv = 0.0;
+    }
+    const double rcp_m = 1.0 / (double)p.m_total32;
+    const double dt = p.dt, rc_dt = 1.0 / p.dt;
+    Drone d;
+    drone_reset(p, d);
+    trig_update(d);
+    long long score = q.timesteps; // collect_coins.py:277
+    int target = 0, steps = 0, coins = 0;
+    bool active = exists;
+    double a_last[6] = {0, 0, 0, 0, 0, 0};
+
+    auto publish_pid = [&](int status) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) d.coin[k] = q.coin_pos[target][k];
+        const double dist = sqrt(coin_dist2(d));
+        int4 lo, hi;
+        lo.x = (int)(unsigned)(score & 0xffffffffLL);
+        lo.y = (int)(score >> 32);
+        lo.z = coins;
+        lo.w = steps;
+        hi.x = status;
+        hi.y = 0;
+        hi.z = __double2loint(dist);
+        hi.w = __double2hiint(dist);
+        int4* out = reinterpret_cast<int4*>(records + i);
+        out[0] = lo;
+        out[1] = hi;
+        if (final_state) write_state(d, a_last, final_state + i * LD_STATE_LEN);
+    };
+
+    for (int t = 0; t < q.timesteps; ++t) {
+        if (!__any_sync(0xffffffffu, active)) break;
+        // :279-292 — step cost, coin test on the current target, exit when all targets are collected
+        score += active ? q.step_reward : 0;
+        steps += active ? 1 : 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) d.coin[k] = q.coin_pos[target][k];
+        const bool hit = active && (coin_dist2(d) < q.coin_thr2[target]);
+        score += hit ? q.coin_value[target] : 0;
+        coins += hit ? 1 : 0;
+        const int next = target + (hit ? 1 : 0);
+        if (active && next >= q.n_coins) {
+            publish_pid(LD_STATUS_FINISHED);
+            active = false;
+        }
+        target = next < q.n_coins ? next : target; // :294-311, setpoints follow the new target
+        double set[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) set[k] = q.coin_pos[target][k];
+        // :328-341 — physics + integrator (no crash rule in this script)
+        int u;
+        physics_step<EXTRAS>(p, d, rcp_m, a_last, u);
+        trig_update(d);
+        // drone/onboard_computer.py:50-85 — cascaded PIDs
+        double lin_out[3], rot_out[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) lin_out[k] = pid_calculate(pid[k], set[k], d.x[k], dt, rc_dt, q.integral_range, q.out_lo[k], q.out_hi[k]);
+        const double rset[3] = {-lin_out[1], lin_out[0], q.yaw_setpoint};
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            rot_out[k] = pid_calculate(pid[3 + k], rset[k], d.x[3 + k], dt, rc_dt, q.integral_range, q.out_lo[3 + k], q.out_hi[3 + k]);
+        // :87-118 — mixer: tilt-compensated base thrust, double clip to [0, 1]
+        const double base = q.base_thrust + lin_out[2];
+        const double cc = d.trig.cr * d.trig.cp; // math.cos(roll) * math.cos(pitch) of the NEW angles
+        double bt = base * div_by(1.0, cc, recip(cc));
+        bt = bt > 1.0 ? 1.0 : bt;
+        bt = bt < 0.0 ? 0.0 : bt;
+        const double r0 = rot_out[0], r1 = rot_out[1], r2 = rot_out[2];
+        const double des[4] = {(r0 - r1) - r2, (-r0 - r1) + r2, (-r0 + r1) - r2, (r0 + r1) + r2}; // physical_model.py:64-66
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double th = bt + des[j];
+            th = th > 1.0 ? 1.0 : th;
+            th = th < 0.0 ? 0.0 : th;
+            d.thrust[j] = th;
+        }
+    }
+    if (active) publish_pid(0);
+}
+
 // ---- accuracy tap for ld_math.cuh (tests/test_gpu_math.py) --------------------------------------
 __global__ void debug_math_kernel(int fn, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ o0,
                                   double* __restrict__ o1, long long n) {
@@ -692,6 +806,51 @@ int ld_reduce_records_device(const ld_record* records, int64_t n, int64_t* stats
     }
     finalize_stats_kernel<<<1, 1, 0, s>>>(st, n);
     LD_CUDA(cudaGetLastError());
+    return LD_OK;
+}
+
+int ld_fly_pid_f64_device(const ld_params* params, const ld_pid_params* pid, const double* pid_gains, int64_t n,
+                          ld_record* records, double* final_state, void* stream) {
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (!pid || pid->n_coins < 1 || pid->n_coins > LD_PID_MAX_COINS || pid->timesteps < 0)
+        return fail(LD_ERR_INVALID_ARG, "bad ld_pid_params");
+    if (n < 0) return fail(LD_ERR_INVALID_ARG, "n < 0");
+    if (n == 0) return LD_OK;
+    if (!pid_gains || !records) return fail(LD_ERR_INVALID_ARG, "NULL device buffer");
+    if (reinterpret_cast<uintptr_t>(records) & 15u) return fail(LD_ERR_INVALID_ARG, "records must be 16-byte aligned");
+    rc = ensure_device();
+    if (rc) return rc;
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    if (has_extras(params))
+        fly_pid_f64_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(*params, *pid, pid_gains, n, records, final_state);
+    else
+        fly_pid_f64_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(*params, *pid, pid_gains, n, records, final_state);
+    LD_CUDA(cudaGetLastError());
+    return LD_OK;
+}
+
+int ld_fly_pid_f64_host(const ld_params* params, const ld_pid_params* pid, const double* pid_gains, int64_t n,
+                        ld_record* records, double* final_state) {
+    if (n < 0) return fail(LD_ERR_INVALID_ARG, "n < 0");
+    if (n == 0) return LD_OK;
+    if (!pid_gains || !records) return fail(LD_ERR_INVALID_ARG, "NULL host buffer");
+    double *d_gains = nullptr, *d_state = nullptr;
+    ld_record* d_rec = nullptr;
+    LD_CUDA(cudaMalloc((void**)&d_gains, (size_t)n * 18 * sizeof(double)));
+    LD_CUDA(cudaMalloc((void**)&d_rec, (size_t)n * sizeof(ld_record)));
+    if (final_state) LD_CUDA(cudaMalloc((void**)&d_state, (size_t)n * LD_STATE_LEN * sizeof(double)));
+    int rc = LD_OK;
+    cudaError_t e = cudaMemcpy(d_gains, pid_gains, (size_t)n * 18 * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) rc = ld_fly_pid_f64_device(params, pid, d_gains, n, d_rec, d_state, nullptr);
+    if (e == cudaSuccess && rc == LD_OK) e = cudaMemcpy(records, d_rec, (size_t)n * sizeof(ld_record), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rc == LD_OK && final_state)
+        e = cudaMemcpy(final_state, d_state, (size_t)n * LD_STATE_LEN * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d_gains);
+    cudaFree(d_rec);
+    if (d_state) cudaFree(d_state);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(LD_ERR_CUDA, "ld_fly_pid_f64_host", e);
     return LD_OK;
 }
 

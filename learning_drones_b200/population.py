@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._abi import GENOME_LEN, RECORD_DTYPE, STATE_LEN, LdParams, make_params
+from ._abi import GENOME_LEN, RECORD_DTYPE, STATE_LEN, LdParams, LdPidParams, make_params, make_pid_params
 
 RECORD_WORDS = RECORD_DTYPE.itemsize // 8  # records travel as int64[n][4] on the torch side
 
@@ -133,3 +133,38 @@ def trace_drone(genome, params: LdParams = None, **kw):
         _lib.check(L.ld_fly_mlp_f64_trace_device(C.byref(p), g.data_ptr(), rec.data_ptr(), tr.data_ptr(), stream))
     r = records_to_numpy(rec)[0]
     return r, tr.cpu().numpy()[: int(r["flight_time"])]
+
+
+# ---- PID controller mode (flight/collect_coins.py as a batch over gain sets) ---------------------
+def fly_pid_population_host(pid_gains, params: LdParams = None, pid: LdPidParams = None, want_state: bool = False):
+    """pid_gains: (n, 6, 3) per-controller (kp, ki, kd) — see _abi.paramset_to_pid_gains — in HOST memory.
+    Returns (records[n], state|None); records['reward'] is the script's final score."""
+    L = _lib.load()
+    p = make_params() if params is None else params
+    q = make_pid_params() if pid is None else pid
+    g = np.ascontiguousarray(pid_gains, dtype=np.float64)
+    if g.ndim != 3 or g.shape[1:] != (6, 3):
+        raise ValueError(f"pid_gains must have shape (n, 6, 3), got {g.shape}")
+    n = g.shape[0]
+    rec = np.empty(n, dtype=RECORD_DTYPE)
+    st = np.empty((n, STATE_LEN), dtype=np.float64) if want_state else None
+    _lib.check(L.ld_fly_pid_f64_host(C.byref(p), C.byref(q), g.ctypes.data, n, rec.ctypes.data, st.ctypes.data if want_state else None))
+    return rec, st
+
+
+def fly_pid_population_device(pid_gains, params: LdParams = None, pid: LdPidParams = None, want_state: bool = False):
+    """CUDA float64 tensor (n, 6, 3) -> (records int64[n][4], state|None); asynchronous on the current stream."""
+    import torch
+
+    L = _lib.load()
+    p = make_params() if params is None else params
+    q = make_pid_params() if pid is None else pid
+    if not (pid_gains.is_cuda and pid_gains.dtype == torch.float64 and pid_gains.is_contiguous() and tuple(pid_gains.shape[1:]) == (6, 3)):
+        raise ValueError("pid_gains must be a contiguous CUDA float64 tensor of shape (n, 6, 3)")
+    n, dev = pid_gains.shape[0], pid_gains.device
+    with torch.cuda.device(dev):
+        records = torch.empty((n, RECORD_WORDS), dtype=torch.int64, device=dev)
+        state = torch.empty((n, STATE_LEN), dtype=torch.float64, device=dev) if want_state else None
+        _lib.check(L.ld_fly_pid_f64_device(C.byref(p), C.byref(q), pid_gains.data_ptr(), n, records.data_ptr(),
+                                           state.data_ptr() if want_state else None, torch.cuda.current_stream(dev).cuda_stream))
+    return records, state

@@ -206,5 +206,154 @@ def main():
     print(f"goldens written to {out_dir} in {time.time() - t0:.1f}s")
 
 
+# ---- PID mode (config 1): flight/collect_coins.py ----------------------------------------------
+PID_PARAMSETS = ["00", "01", "02", "10", "11", "12", "13", "20", "21", "22"]
+PID_COINS = [[0.0, 0.0, 5.0], [25.0, 25.0, 5.0], [-10.0, 35.0, 5.0], [0.0, 0.0, 5.0]]  # collect_coins.py:253-258
+
+
+def _import_reference_pid():
+    _import_reference()
+    with contextlib.redirect_stdout(io.StringIO()):
+        from drone.controller.pid import PID
+        from drone.onboard_computer import PIDControlUNnit
+        from drone.quadcopter import choose_paramset, parameters
+        from drone.quadcopter.physical_model import QuadcopterPhysics
+        from drone.sensor.sensor import Sensor, get_positions_and_angles
+        from objects.coins import Coin
+    # SURVEY §8c second shim: numpy >= 1.24 refuses the ragged array the cascade builds from
+    # shape-(1,) setpoints (onboard_computer.py:74-81); numpy 1.17 scalar-converted them.
+    if not getattr(PID, "_ld_shim", False):
+        orig = PID.set_setpoint
+
+        def set_setpoint(self, point):
+            orig(self, float(np.asarray(point).reshape(-1)[0]) if isinstance(point, np.ndarray) else point)
+
+        PID.set_setpoint = set_setpoint
+        PID._ld_shim = True
+    return PID, PIDControlUNnit, choose_paramset, parameters, QuadcopterPhysics, Sensor, get_positions_and_angles, Coin
+
+
+def pid_gains(paramset):
+    """18 gains in choose_paramset.convert_paramset_2_float order."""
+    cp = _import_reference_pid()[2]
+    return np.array(cp.convert_paramset_2_float(cp.get_paramset(paramset)), dtype=np.float64)
+
+
+def ref_fly_pid(args):
+    """The main loop of flight/collect_coins.py:125-364 driven through the reference's own PID,
+    PIDControlUNnit, QuadcopterPhysics, Sensor and Coin classes (the script itself is a __main__
+    block with prints and sleeps; `run_collect_coins_script` runs it verbatim once as a cross-check)."""
+    gains, timesteps, want_trace = args
+    PID, PIDControlUNnit, cp, P, QuadcopterPhysics, Sensor, get_positions_and_angles, Coin = _import_reference_pid()
+    (kp_x, kp_y, kp_z, ki_x, ki_y, ki_z, kd_x, kd_y, kd_z, kp_rol, kp_pit, kp_yaw, ki_rol, ki_pit, ki_yaw, kd_rol, kd_pit, kd_yaw) = [float(v) for v in gains]
+    delta_t = 0.01
+    lim = [-np.pi / 4, np.pi / 4]
+    mk = lambda kp, ki, kd, **kw: PID(kp=kp, ki=ki, kd=kd, timeStep=delta_t, setValue=0, integralRange=2, calculateFlag="signChange", **kw)
+    rot_pids = [mk(kp_rol, ki_rol, kd_rol, outputLimitRange=lim), mk(kp_pit, ki_pit, kd_pit, outputLimitRange=lim),
+                mk(kp_yaw, ki_yaw, kd_yaw, outputLimitRange=[-np.pi / 6, np.pi / 6])]
+    lin_pids = [mk(kp_x, ki_x, kd_x, outputLimitRange=lim), mk(kp_y, ki_y, kd_y, outputLimitRange=lim),
+                mk(kp_z, ki_y, kd_z)]  # collect_coins.py:181 uses ki_y for the z PID
+    for pid, sv in zip(lin_pids, (10, 10, 10)):
+        pid.setValue = sv
+    qc = QuadcopterPhysics(mass_center=P.mass_center, mass_motor=P.mass_motor, radius_motor_center=P.radius_motor_center,
+                           coef_force=P.coef_force, coef_moment=P.coef_moment, coef_wind=P.coef_wind, gravity=P.gravity,
+                           mass_payload=P.mass_payload, x_payload=P.x_payload, y_payload=P.y_payload, I_x=P.I_x, I_y=P.I_y, I_z=P.I_z)
+    controller = PIDControlUNnit(np.concatenate([lin_pids, rot_pids]), qc)
+    initial_pos = np.array([[0.0, 0.0, 10.0]]).T
+    zeros = np.array([[0.0, 0.0, 0.0]]).T
+    sensors = [Sensor(delta_t, initial_pos[i, 0], 0.0) for i in range(3)] + [Sensor(delta_t, 0.0, 0.0) for _ in range(3)]
+    wind, lab_pos, vel, angle, angle_vel = zeros.copy(), initial_pos, zeros.copy(), zeros.copy(), zeros.copy()
+    thrust = np.array([[0, 0, 0, 0]]).T
+    coins = [Coin(np.asarray([c]).T, 1, value=1000) for c in PID_COINS]
+    target_index = new_target_index = 0
+    score = timesteps
+    steps, pick_steps, trace, finished = 0, [], [], False
+    for time_i in range(timesteps):
+        score -= 1
+        steps += 1
+        if coins[target_index].is_in_vicinity(lab_pos):
+            score += coins[target_index].value
+            new_target_index = target_index + 1
+            pick_steps.append(time_i)
+        if new_target_index >= len(coins):
+            finished = True
+            break
+        rot_targets = np.zeros((3, 1))
+        lin_targets = coins[new_target_index].position
+        [rot_pids[i].set_setpoint(rot_targets[i, 0]) for i in range(3)]
+        [lin_pids[i].set_setpoint(lin_targets[i, 0]) for i in range(3)]
+        target_index = new_target_index
+        lin_acc, rot_acc = qc.calculate_accelerations(angle, wind, thrust, lin_acc_drone_2_lab=True)
+        [sensors[i].measure_acceleration(lin_acc[i, 0]) for i in range(3)]
+        [sensors[i].measure_acceleration(rot_acc[i - 3, 0]) for i in range(3, 6)]
+        lab_pos, vel, angle, angle_vel = get_positions_and_angles(sensors)
+        thrust = controller.translate_input_to_thrust(lab_pos, vel, angle, angle_vel, angle, lin_pids, rot_pids)
+        if want_trace:
+            trace.append(np.concatenate([lab_pos.ravel(), vel.ravel(), angle.ravel(), angle_vel.ravel(),
+                                         [s.current_acceleration for s in sensors], [s.last_acceleration for s in sensors],
+                                         np.asarray(thrust, dtype=np.float64).ravel()]))
+    state = np.concatenate([lab_pos.ravel(), vel.ravel(), angle.ravel(), angle_vel.ravel(),
+                            [s.current_acceleration for s in sensors], [s.last_acceleration for s in sensors],
+                            np.asarray(thrust, dtype=np.float64).ravel()]).astype(np.float64)
+    return dict(score=int(score), steps=steps, coins=len(pick_steps), finished=finished, pick_steps=pick_steps, state=state,
+                trace=np.array(trace) if want_trace else None)
+
+
+def run_collect_coins_script(paramset="11"):
+    """Run the reference's flight/collect_coins.py verbatim (headless) and return its printed Final Score."""
+    import re
+    import runpy
+    import time as _time
+
+    _import_reference_pid()
+    out = io.StringIO()
+    argv, sleep = sys.argv, _time.sleep
+    sys.argv = ["collect_coins.py", "65432", "0", "0", paramset]
+    _time.sleep = lambda s: None
+    try:
+        with contextlib.redirect_stdout(out):
+            runpy.run_path(os.path.join(REF, "flight", "collect_coins.py"), run_name="__main__")
+    except (SystemExit, AttributeError):  # dh.finish() touches self.conn, undefined when not visualising
+        pass
+    finally:
+        sys.argv, _time.sleep = argv, sleep
+    m = re.search(r"Final Score: (-?\d+)", out.getvalue())
+    return int(m.group(1)) if m else None
+
+
+def main_pid(out_dir, pool):
+    rng = np.random.default_rng(11)
+    gains = [pid_gains(ps) for ps in PID_PARAMSETS]
+    # plus perturbed copies of paramset 11 (a "batch of gain sets", SURVEY §8f-2)
+    base = pid_gains("11")
+    gains += [base * rng.uniform(0.7, 1.3, size=18) for _ in range(54)]
+    gains = np.array(gains)
+    jobs = [(g, 3500, i == 4) for i, g in enumerate(gains)]
+    res = pool.map(ref_fly_pid, jobs, chunksize=1) if pool else [ref_fly_pid(j) for j in jobs]
+    script_score = run_collect_coins_script("11")
+    pick = np.full((len(res), 4), -1, dtype=np.int32)
+    for i, r in enumerate(res):
+        pick[i, : len(r["pick_steps"])] = r["pick_steps"]
+    np.savez_compressed(
+        os.path.join(out_dir, "pid_collect_coins.npz"), gains=gains, paramsets=np.array(PID_PARAMSETS), timesteps=np.int64(3500),
+        score=np.array([r["score"] for r in res], dtype=np.int64), steps=np.array([r["steps"] for r in res], dtype=np.int32),
+        coins=np.array([r["coins"] for r in res], dtype=np.int32), finished=np.array([r["finished"] for r in res]),
+        pick_steps=pick, state=np.array([r["state"] for r in res]), trace11=res[4]["trace"],
+        script_final_score_11=np.int64(-1 if script_score is None else script_score))
+    print("pid goldens:", [(ps, r["score"], r["steps"]) for ps, r in zip(PID_PARAMSETS, res)], "script(11) =", script_score)
+
+
+if __name__ == "__main__" and "--pid-only" in sys.argv:
+    sys.argv.remove("--pid-only")
+    _out = os.path.join(ROOT, "tests", "golden")
+    _scratch = tempfile.mkdtemp(prefix="ld_golden_")
+    os.chdir(_scratch)
+    os.makedirs("translation/triple/11", exist_ok=True)
+    import multiprocessing as _mp
+
+    main_pid(_out, _mp.get_context("fork").Pool(os.cpu_count()))
+    sys.exit(0)
+
+
 if __name__ == "__main__":
     main()

@@ -323,6 +323,133 @@ int ld_oracle_trace_mlp(const ld_params* p, const double* genome, ld_record* rec
     return LD_OK;
 }
 
+/* ---- PID mode: flight/collect_coins.py:278-364 ---------------------------------------------- */
+typedef struct {
+    double kp, ki, kd, set, I, prev_e, prev_pv, lo, hi;
+} od_pid;
+
+/* drone/controller/pid.py:77-106 (calculate_error_sign), :132-134, :136-142 */
+static double pid_calculate(od_pid* c, double pv, double dt, double range) {
+    double error = c->set - pv;
+    if (c->prev_e * error < 0) c->I = 0;
+    if (fabs(error) < range) c->I += error;
+    double diff = (c->prev_pv != 0) ? pv - c->prev_pv : 0;
+    double out = c->kp * error + c->ki * c->I * dt - c->kd * diff / dt;
+    c->prev_pv = pv;
+    if (error != 0) c->prev_e = error;
+    if (out < c->lo) out = c->lo;
+    else if (out > c->hi) out = c->hi;
+    return out;
+}
+
+static void fly_pid(const ld_params* p, const ld_pid_params* q, const double* gains, od_drone* d, double* trace, int use_fma) {
+    drone_reset(p, d);
+    od_pid pid[6]; /* x y z roll pitch yaw */
+    for (int i = 0; i < 6; ++i) {
+        pid[i].kp = gains[3 * i];
+        pid[i].ki = gains[3 * i + 1];
+        pid[i].kd = gains[3 * i + 2];
+        pid[i].set = 0;
+        pid[i].I = pid[i].prev_e = pid[i].prev_pv = 0;
+        pid[i].lo = q->out_lo[i];
+        pid[i].hi = q->out_hi[i];
+    }
+    static const double A[4][3] = {{1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {1, 1, 1}}; /* physical_model.py:64-66 */
+    int target = 0;
+    d->reward = q->timesteps; /* collect_coins.py:277 */
+    for (int i = 0; i < 3; ++i) d->coin[i] = q->coin_pos[0][i];
+    for (int t = 0; t < q->timesteps; ++t) {
+        d->reward += q->step_reward; /* :279 */
+        d->flight_time += 1;
+        int next = target;
+        double x[3] = {q->coin_pos[target][0] - d->pos[0], q->coin_pos[target][1] - d->pos[1], q->coin_pos[target][2] - d->pos[2]};
+        if (dot_n(x, x, 3, use_fma) < q->coin_thr2[target]) { /* :284-287, sqrt(s) < r <=> s < thr2 */
+            d->reward += q->coin_value[target];
+            d->coins += 1;
+            next = target + 1;
+        }
+        if (next >= q->n_coins) { /* :289-292 */
+            d->status |= LD_STATUS_FINISHED;
+            break;
+        }
+        target = next; /* :294-311 */
+        for (int i = 0; i < 3; ++i) d->coin[i] = q->coin_pos[target][i];
+        double lin[3], rot[3];
+        accelerations(p, d->ang, d->thrust, lin, rot, use_fma); /* :328-330 */
+        integrate(p, d, lin, rot);                              /* :335-341 */
+        /* onboard_computer.py:50-85 */
+        double lin_out[3], rot_out[3];
+        for (int i = 0; i < 3; ++i) {
+            pid[i].set = d->coin[i];
+            lin_out[i] = pid_calculate(&pid[i], d->pos[i], p->dt, q->integral_range);
+        }
+        pid[3].set = -lin_out[1];
+        pid[4].set = lin_out[0];
+        pid[5].set = q->yaw_setpoint;
+        for (int i = 0; i < 3; ++i) rot_out[i] = pid_calculate(&pid[3 + i], d->ang[i], p->dt, q->integral_range);
+        /* onboard_computer.py:87-118 */
+        double base = q->base_thrust + lin_out[2];
+        double ratio = 1 / (cos(d->ang[0]) * cos(d->ang[1]));
+        double bt = base * ratio;
+        if (bt > 1) bt = 1;
+        if (bt < 0) bt = 0;
+        for (int j = 0; j < 4; ++j) {
+            double desired = (A[j][0] * rot_out[0] + A[j][1] * rot_out[1]) + A[j][2] * rot_out[2];
+            double th = bt + desired;
+            if (th > 1) th = 1;
+            if (th < 0) th = 0;
+            d->thrust[j] = th;
+        }
+        if (trace) state_row(d, trace + (size_t)t * LD_STATE_LEN);
+    }
+    d->distance = coin_distance(d, use_fma);
+}
+
+typedef struct {
+    const ld_params* p;
+    const ld_pid_params* q;
+    const double* gains;
+    int64_t n;
+    ld_record* records;
+    double* final_state;
+    int use_fma;
+    atomic_llong* next;
+} od_pid_job;
+
+static void* od_pid_worker(void* arg) {
+    od_pid_job* j = (od_pid_job*)arg;
+    for (;;) {
+        int64_t i = atomic_fetch_add(j->next, 1);
+        if (i >= j->n) break;
+        od_drone d;
+        fly_pid(j->p, j->q, j->gains + i * 18, &d, NULL, j->use_fma);
+        emit(&d, j->records + i, j->final_state ? j->final_state + i * LD_STATE_LEN : NULL);
+    }
+    return NULL;
+}
+
+int ld_oracle_fly_pid(const ld_params* p, const ld_pid_params* q, const double* gains, int64_t n, ld_record* records,
+                      double* final_state, double* trace, int use_fma, int nthreads) {
+    if (!p || !q || !gains || !records || n < 0 || q->n_coins < 1 || q->n_coins > LD_PID_MAX_COINS) return LD_ERR_INVALID_ARG;
+    if (trace) {
+        od_drone d;
+        fly_pid(p, q, gains, &d, trace, use_fma);
+        emit(&d, records, final_state);
+        return LD_OK;
+    }
+    if (nthreads <= 0) nthreads = ld_oracle_max_threads();
+    if (nthreads > 256) nthreads = 256;
+    atomic_llong next = 0;
+    od_pid_job job = {p, q, gains, n, records, final_state, use_fma, &next};
+    pthread_t tid[256];
+    int started = 0;
+    for (int t = 1; t < nthreads; ++t)
+        if (pthread_create(&tid[started], NULL, od_pid_worker, &job) == 0) ++started;
+    od_pid_worker(&job);
+    for (int t = 0; t < started; ++t) pthread_join(tid[t], NULL);
+    return LD_OK;
+}
+
 /* single calculate_accelerations() call, for unit tests against the reference */
 int ld_oracle_accelerations(const ld_params* p, const double* angle3, const double* thrust4, double* lin3,
                             double* rot3, int use_fma) {

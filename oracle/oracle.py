@@ -11,7 +11,7 @@ import subprocess
 
 import numpy as np
 
-from learning_drones_b200._abi import GENOME_LEN, RECORD_DTYPE, STATE_LEN, LdParams, LdRecord
+from learning_drones_b200._abi import GENOME_LEN, RECORD_DTYPE, STATE_LEN, LdParams, LdPidParams, LdRecord
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libld_oracle.so")
@@ -43,6 +43,8 @@ def lib():
         L.ld_oracle_accelerations.argtypes = [C.POINTER(LdParams), dp, dp, dp, dp, C.c_int]
         L.ld_oracle_accelerations.restype = C.c_int
         L.ld_oracle_max_threads.restype = C.c_int
+        L.ld_oracle_fly_pid.argtypes = [C.POINTER(LdParams), C.POINTER(LdPidParams), dp, C.c_int64, C.POINTER(LdRecord), dp, dp, C.c_int, C.c_int]
+        L.ld_oracle_fly_pid.restype = C.c_int
         _lib = L
     return _lib
 
@@ -93,3 +95,18 @@ def accelerations(params: LdParams, angle, thrust, use_fma: bool = True):
     rot = np.zeros(3)
     lib().ld_oracle_accelerations(C.byref(params), _dptr(a), _dptr(t), _dptr(lin), _dptr(rot), int(use_fma))
     return lin, rot
+
+
+def fly_pid(params: LdParams, pid: LdPidParams, pid_gains, use_fma: bool = True, nthreads: int = 0, want_state: bool = False,
+            want_trace: bool = False):
+    """Batch of flight/collect_coins.py episodes; pid_gains (n, 6, 3). Returns (records, state|None, trace|None)."""
+    g = np.ascontiguousarray(pid_gains, dtype=np.float64).reshape(-1, 18)
+    n = g.shape[0]
+    rec = np.zeros(n, dtype=RECORD_DTYPE)
+    st = np.zeros((n, STATE_LEN)) if want_state else None
+    tr = np.full((int(pid.timesteps), STATE_LEN), np.nan) if want_trace else None
+    rc = lib().ld_oracle_fly_pid(C.byref(params), C.byref(pid), _dptr(g), n, rec.ctypes.data_as(C.POINTER(LdRecord)),
+                                 _dptr(st) if want_state else None, _dptr(tr) if want_trace else None, int(use_fma), int(nthreads))
+    if rc != 0:
+        raise RuntimeError(f"ld_oracle_fly_pid failed: {rc}")
+    return rec, st, tr
