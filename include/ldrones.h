@@ -187,6 +187,34 @@ int ld_fly_pid_f64_device(const ld_params* params, const ld_pid_params* pid, con
 int ld_fly_pid_f64_host(const ld_params* params, const ld_pid_params* pid, const double* pid_gains, int64_t n,
                         ld_record* records, double* final_state);
 
+/* ---- GA step: evolve/util.py:5-78 + drone/drone.py:167-172 on the genome matrix --
+ * For every pair slot (c, c+1), c even, of the NEW population: four uniform parent indices, two
+ * 2-way tournaments on `reward` (with probability p_tournament the better one wins, else the
+ * worse; "better" = strictly greater reward, ties -> second index, util.py:30-45), children =
+ * copies of the winners, then per LAYER with probability p_crossover a single-point crossover
+ * of the C-order-flattened layer (util.py:48-78), then per weight with probability
+ * mutation_rate `+= N(0, mutation_sigma)` (drone.py:167-172).
+ * Randomness is Philox4x32-10 keyed by (seed, generation, slot): every rank derives the same
+ * selections without communication.  It is NOT numpy's MT19937 stream (out of scope).
+ *
+ * parents      [n][LD_GENOME_LEN]   whole current population (device)
+ * records      [n]                  fitness of the current population (reward field is used)
+ * children     [hi-lo][LD_GENOME_LEN] rows lo..hi-1 of the new population (lo, hi even)
+ * Elitism (evolve/evolution.py:105-107: slot 0 <- unmutated all-time best) is a row copy the
+ * caller does afterwards. */
+typedef struct ld_ga_params {
+    uint64_t seed;
+    uint32_t generation;
+    uint32_t _pad;
+    double p_tournament;   /* 0.6  evolve/evolution.py:19 */
+    double p_crossover;    /* 0.05 :20 */
+    double mutation_rate;  /* 0.05 :18 */
+    double mutation_sigma; /* 0.3  drone/drone.py:172 */
+} ld_ga_params;
+
+int ld_ga_step_device(const ld_ga_params* ga, const double* parents, const ld_record* records, int64_t n,
+                      double* children, int64_t lo, int64_t hi, void* stream);
+
 /* ---- population statistics (warp-shuffle reductions) ----------------------
  * stats[0]=sum flight_time (active drone-steps), [1]=max reward, [2]=argmax reward
  * (lowest index wins ties, like np.argmax at evolve/evolution.py:77),

@@ -250,3 +250,25 @@ def paramset_to_pid_gains(paramset18) -> np.ndarray:
     kp_x, kp_y, kp_z, ki_x, ki_y, ki_z, kd_x, kd_y, kd_z, kp_r, kp_p, kp_w, ki_r, ki_p, ki_w, kd_r, kd_p, kd_w = np.moveaxis(g, -1, 0)
     rows = [(kp_x, ki_x, kd_x), (kp_y, ki_y, kd_y), (kp_z, ki_y, kd_z), (kp_r, ki_r, kd_r), (kp_p, ki_p, kd_p), (kp_w, ki_w, kd_w)]
     return np.ascontiguousarray(np.stack([np.stack(r, axis=-1) for r in rows], axis=-2))
+
+
+class LdGaParams(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint64),
+        ("generation", C.c_uint32),
+        ("_pad", C.c_uint32),
+        ("p_tournament", C.c_double),
+        ("p_crossover", C.c_double),
+        ("mutation_rate", C.c_double),
+        ("mutation_sigma", C.c_double),
+    ]
+
+
+def make_ga_params(seed: int, generation: int, p_tournament: float = 0.6, p_crossover: float = 0.05,
+                   mutation_rate: float = 0.05, mutation_sigma: float = 0.3) -> LdGaParams:
+    """Hyper-parameters of evolve/evolution.py:16-20 and drone/drone.py:172."""
+    g = LdGaParams()
+    g.seed, g.generation = int(seed) & (2**64 - 1), int(generation)
+    g.p_tournament, g.p_crossover = float(p_tournament), float(p_crossover)
+    g.mutation_rate, g.mutation_sigma = float(mutation_rate), float(mutation_sigma)
+    return g

@@ -494,6 +494,87 @@ fly_pid_f64_kernel(const __grid_constant__ ld_params p, const __grid_constant__ 
     if (active) publish_pid(0);
 }
 
+// ---- GA step: evolve/util.py:5-78 + drone/drone.py:167-172, one warp per pair of children --------
+struct U4 {
+    uint32_t v[4];
+};
+
+__device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    U4 o;
+    o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
+    return o;
+}
+
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+    return (double)((((unsigned long long)hi << 32) | lo) >> 11) * 0x1.0p-53;
+}
+
+constexpr uint32_t kStreamSelect = 1, kStreamMutate = 2;
+
+__global__ void __launch_bounds__(256)
+ga_step_kernel(const __grid_constant__ ld_ga_params ga, const double* __restrict__ parents, const ld_record* __restrict__ records,
+               long long n, double* __restrict__ children, long long lo, long long hi) {
+    const uint32_t k0 = (uint32_t)ga.seed, k1 = (uint32_t)(ga.seed >> 32), gen = ga.generation;
+    const unsigned lane = threadIdx.x & 31u;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long c = lo + 2 * ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); c < hi; c += 2 * warps) {
+        const uint32_t pair = (uint32_t)(c >> 1);
+        // selection: every lane derives the same draws (counter-based), no shuffles needed
+        const U4 a = philox4x32_10(pair, 0, kStreamSelect, gen, k0, k1), b = philox4x32_10(pair, 1, kStreamSelect, gen, k0, k1);
+        const U4 t = philox4x32_10(pair, 2, kStreamSelect, gen, k0, k1);
+        const long long idx[4] = {(long long)(u53(a.v[0], a.v[1]) * (double)n), (long long)(u53(a.v[2], a.v[3]) * (double)n),
+                                  (long long)(u53(b.v[0], b.v[1]) * (double)n), (long long)(u53(b.v[2], b.v[3]) * (double)n)};
+        const double r[2] = {u53(t.v[0], t.v[1]), u53(t.v[2], t.v[3])};
+        long long win[2];
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const long long i1 = idx[2 * w], i2 = idx[2 * w + 1];
+            const long long s1 = __ldg(reinterpret_cast<const long long*>(records + i1));
+            const long long s2 = __ldg(reinterpret_cast<const long long*>(records + i2));
+            const long long better = s1 > s2 ? i1 : i2, worse = s1 > s2 ? i2 : i1;
+            win[w] = r[w] < ga.p_tournament ? better : worse;
+        }
+        int cut[3];
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            const U4 x = philox4x32_10(pair, 3 + l, kStreamSelect, gen, k0, k1);
+            const int lo_g = l == 0 ? 0 : (l == 1 ? kL1 : kL1 + kL2), genes = l == 0 ? kL1 : (l == 1 ? kL2 : kL3);
+            // cut position in genome coordinates; "no crossover" = cut at the layer's end
+            cut[l] = u53(x.v[0], x.v[1]) < ga.p_crossover ? lo_g + (int)(u53(x.v[2], x.v[3]) * (double)genes) : lo_g + genes;
+        }
+        const double* __restrict__ pa = parents + win[0] * LD_GENOME_LEN;
+        const double* __restrict__ pb = parents + win[1] * LD_GENOME_LEN;
+        double* __restrict__ ca = children + (c - lo) * LD_GENOME_LEN;
+        double* __restrict__ cb = children + (c + 1 - lo) * LD_GENOME_LEN;
+        for (int g = (int)lane; g < LD_GENOME_LEN; g += 32) { // coalesced 256-B row segments
+            const int l = g < kL1 ? 0 : (g < kL1 + kL2 ? 1 : 2);
+            const bool swapped = g >= cut[l]; // tail of a crossed layer comes from the other child
+            double wa = __ldg(pa + g), wb = __ldg(pb + g);
+            double va = swapped ? wb : wa, vb = swapped ? wa : wb;
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const U4 x = philox4x32_10((uint32_t)(c + w), (uint32_t)g, kStreamMutate, gen, k0, k1);
+                if (u53(x.v[0], x.v[1]) < ga.mutation_rate) {
+                    const double u1 = ((double)x.v[2] + 0.5) * 0x1.0p-32, u2 = ((double)x.v[3] + 0.5) * 0x1.0p-32;
+                    const double z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2); // Box-Muller
+                    if (w == 0) va = va + ga.mutation_sigma * z;
+                    else vb = vb + ga.mutation_sigma * z;
+                }
+            }
+            ca[g] = va;
+            cb[g] = vb;
+        }
+    }
+}
+
 // ---- accuracy tap for ld_math.cuh (tests/test_gpu_math.py) --------------------------------------
 __global__ void debug_math_kernel(int fn, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ o0,
                                   double* __restrict__ o1, long long n) {
@@ -851,6 +932,22 @@ int ld_fly_pid_f64_host(const ld_params* params, const ld_pid_params* pid, const
     if (d_state) cudaFree(d_state);
     if (rc) return rc;
     if (e != cudaSuccess) return fail(LD_ERR_CUDA, "ld_fly_pid_f64_host", e);
+    return LD_OK;
+}
+
+int ld_ga_step_device(const ld_ga_params* ga, const double* parents, const ld_record* records, int64_t n, double* children,
+                      int64_t lo, int64_t hi, void* stream) {
+    if (!ga || !parents || !records || !children) return fail(LD_ERR_INVALID_ARG, "NULL argument");
+    if (n < 2 || (n & 1)) return fail(LD_ERR_INVALID_ARG, "population size must be even and >= 2 (evolve/util.py:14-24 pairs slots)");
+    if (lo < 0 || hi > n || lo > hi || (lo & 1) || (hi & 1)) return fail(LD_ERR_INVALID_ARG, "children range [lo, hi) must be even-aligned inside [0, n]");
+    if (lo == hi) return LD_OK;
+    int rc = ensure_device();
+    if (rc) return rc;
+    long long pairs = (hi - lo) / 2;
+    long long blocks = (pairs + 7) / 8;
+    if (blocks > 16LL * g_dev.sms) blocks = 16LL * g_dev.sms;
+    ga_step_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*ga, parents, records, n, children, lo, hi);
+    LD_CUDA(cudaGetLastError());
     return LD_OK;
 }
 

@@ -450,6 +450,80 @@ int ld_oracle_fly_pid(const ld_params* p, const ld_pid_params* q, const double* 
     return LD_OK;
 }
 
+/* ---- GA step: evolve/util.py:5-78, drone/drone.py:167-172 with the library's Philox stream ---- */
+typedef struct { uint32_t v[4]; } od_u4;
+
+static od_u4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    od_u4 o = {{c0, c1, c2, c3}};
+    return o;
+}
+
+static double u53(uint32_t hi, uint32_t lo) { return (double)((((uint64_t)hi << 32) | lo) >> 11) * 0x1.0p-53; }
+
+enum { OD_STREAM_SELECT = 1, OD_STREAM_MUTATE = 2 };
+
+static const int od_layer_off[4] = {0, 160, 270, 314};
+
+int ld_oracle_ga_step(const ld_ga_params* ga, const double* parents, const int64_t* rewards, int64_t n, double* children,
+                      int64_t lo, int64_t hi, int32_t* picks /* [hi-lo][5] or NULL: parent, cut0..2 (-1 none), n_mutated */) {
+    if (!ga || !parents || !rewards || !children || n < 2 || (n & 1) || lo < 0 || hi > n || (lo & 1) || (hi & 1)) return LD_ERR_INVALID_ARG;
+    const uint32_t k0 = (uint32_t)ga->seed, k1 = (uint32_t)(ga->seed >> 32), gen = ga->generation;
+    for (int64_t c = lo; c < hi; c += 2) {
+        const uint32_t pair = (uint32_t)(c >> 1);
+        od_u4 a = philox4x32_10(pair, 0, OD_STREAM_SELECT, gen, k0, k1), b = philox4x32_10(pair, 1, OD_STREAM_SELECT, gen, k0, k1);
+        od_u4 t = philox4x32_10(pair, 2, OD_STREAM_SELECT, gen, k0, k1);
+        int64_t idx[4] = {(int64_t)(u53(a.v[0], a.v[1]) * (double)n), (int64_t)(u53(a.v[2], a.v[3]) * (double)n),
+                          (int64_t)(u53(b.v[0], b.v[1]) * (double)n), (int64_t)(u53(b.v[2], b.v[3]) * (double)n)};
+        double r[2] = {u53(t.v[0], t.v[1]), u53(t.v[2], t.v[3])};
+        int64_t win[2];
+        for (int w = 0; w < 2; ++w) { /* util.py:30-45 */
+            int64_t i1 = idx[2 * w], i2 = idx[2 * w + 1];
+            int64_t better = rewards[i1] > rewards[i2] ? i1 : i2, worse = rewards[i1] > rewards[i2] ? i2 : i1;
+            win[w] = r[w] < ga->p_tournament ? better : worse;
+        }
+        double* ch[2] = {children + (c - lo) * LD_GENOME_LEN, children + (c + 1 - lo) * LD_GENOME_LEN};
+        memcpy(ch[0], parents + win[0] * LD_GENOME_LEN, LD_GENOME_LEN * sizeof(double));
+        memcpy(ch[1], parents + win[1] * LD_GENOME_LEN, LD_GENOME_LEN * sizeof(double));
+        int cuts[3] = {-1, -1, -1};
+        for (int l = 0; l < 3; ++l) { /* util.py:48-78 */
+            od_u4 x = philox4x32_10(pair, 3 + l, OD_STREAM_SELECT, gen, k0, k1);
+            if (u53(x.v[0], x.v[1]) < ga->p_crossover) {
+                int genes = od_layer_off[l + 1] - od_layer_off[l];
+                int cut = (int)(u53(x.v[2], x.v[3]) * (double)genes);
+                cuts[l] = cut;
+                for (int g = od_layer_off[l] + cut; g < od_layer_off[l + 1]; ++g) {
+                    double tmp = ch[0][g];
+                    ch[0][g] = ch[1][g];
+                    ch[1][g] = tmp;
+                }
+            }
+        }
+        for (int w = 0; w < 2; ++w) { /* drone.py:167-172 */
+            int nm = 0;
+            for (int g = 0; g < LD_GENOME_LEN; ++g) {
+                od_u4 x = philox4x32_10((uint32_t)(c + w), (uint32_t)g, OD_STREAM_MUTATE, gen, k0, k1);
+                if (u53(x.v[0], x.v[1]) < ga->mutation_rate) {
+                    double u1 = ((double)x.v[2] + 0.5) * 0x1.0p-32, u2 = ((double)x.v[3] + 0.5) * 0x1.0p-32;
+                    double z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2); /* Box-Muller */
+                    ch[w][g] = ch[w][g] + ga->mutation_sigma * z;
+                    ++nm;
+                }
+            }
+            if (picks) {
+                int32_t* pk = picks + (c + w - lo) * 5;
+                pk[0] = (int32_t)win[w]; pk[1] = cuts[0]; pk[2] = cuts[1]; pk[3] = cuts[2]; pk[4] = nm;
+            }
+        }
+    }
+    return LD_OK;
+}
+
 /* single calculate_accelerations() call, for unit tests against the reference */
 int ld_oracle_accelerations(const ld_params* p, const double* angle3, const double* thrust4, double* lin3,
                             double* rot3, int use_fma) {

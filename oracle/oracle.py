@@ -11,7 +11,7 @@ import subprocess
 
 import numpy as np
 
-from learning_drones_b200._abi import GENOME_LEN, RECORD_DTYPE, STATE_LEN, LdParams, LdPidParams, LdRecord
+from learning_drones_b200._abi import GENOME_LEN, RECORD_DTYPE, STATE_LEN, LdGaParams, LdParams, LdPidParams, LdRecord
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libld_oracle.so")
@@ -45,6 +45,9 @@ def lib():
         L.ld_oracle_max_threads.restype = C.c_int
         L.ld_oracle_fly_pid.argtypes = [C.POINTER(LdParams), C.POINTER(LdPidParams), dp, C.c_int64, C.POINTER(LdRecord), dp, dp, C.c_int, C.c_int]
         L.ld_oracle_fly_pid.restype = C.c_int
+        L.ld_oracle_ga_step.argtypes = [C.POINTER(LdGaParams), dp, C.POINTER(C.c_int64), C.c_int64, dp, C.c_int64, C.c_int64,
+                                        C.POINTER(C.c_int32)]
+        L.ld_oracle_ga_step.restype = C.c_int
         _lib = L
     return _lib
 
@@ -110,3 +113,19 @@ def fly_pid(params: LdParams, pid: LdPidParams, pid_gains, use_fma: bool = True,
     if rc != 0:
         raise RuntimeError(f"ld_oracle_fly_pid failed: {rc}")
     return rec, st, tr
+
+
+def ga_step(ga: LdGaParams, parents, rewards, lo: int = 0, hi: int = None):
+    """evolve/util.selection_and_crossover + Drone.mutate on the genome matrix with the library's
+    Philox stream. Returns (children[hi-lo][314], picks[hi-lo][5] = parent, cut0..2 (-1 none), n_mutated)."""
+    g = np.ascontiguousarray(parents, dtype=np.float64).reshape(-1, GENOME_LEN)
+    n = g.shape[0]
+    hi = n if hi is None else hi
+    r = np.ascontiguousarray(rewards, dtype=np.int64)
+    out = np.zeros((hi - lo, GENOME_LEN))
+    picks = np.zeros((hi - lo, 5), dtype=np.int32)
+    rc = lib().ld_oracle_ga_step(C.byref(ga), _dptr(g), r.ctypes.data_as(C.POINTER(C.c_int64)), n, _dptr(out), lo, hi,
+                                 picks.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != 0:
+        raise RuntimeError(f"ld_oracle_ga_step failed: {rc}")
+    return out, picks
