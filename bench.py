@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--timesteps", type=int, default=2000)
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--generations", type=int, default=5, help="generations of the full GA loop to time (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -282,6 +283,31 @@ def main():
     assert out_np.tobytes() == rec_np.tobytes(), "host-API result differs from device-API result"
     e2e_value = active_steps * args.steps / e2e_s
 
+    # ---- generations/s: full loop (fly + record all-gather + best tracking + GA step + elitism) ----
+    gens = None
+    if args.generations > 0:
+        from learning_drones_b200.evolve.gpu import GpuEvolution
+
+        ev = GpuEvolution(population(args.population, D * world), seed=2026, timesteps=H)
+        ev.step()  # warm (allocations, NCCL)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        hist = ev.run(args.generations)
+        g1.record()
+        barrier()
+        gms = g0.elapsed_time(g1)
+        if world > 1:
+            tt = torch.tensor([gms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            gms = float(tt.item())
+        gens = {"value": args.generations / (gms * 1e-3), "unit": "generations/s", "generations": args.generations,
+                "population": D * world, "timesteps": H,
+                "active_drone_steps_per_generation": [h["active_steps"] for h in hist],
+                "best_score": [h["global_best_score"] for h in hist],
+                "note": "generation 0 = the bench population, later generations = its GA offspring (most crash early)"}
+        del ev
+
     if rank == 0:
         peaks, peaks_src = measured_peaks()
         tf = __import__("ctypes").c_double()
@@ -315,6 +341,8 @@ def main():
             "gpu_launches": args.steps * world,
             "clocks": clocks,
         }
+        if gens is not None:
+            line["generations"] = gens
         if not args.no_cpu_baseline and world == 1:
             sample = args.cpu_sample or 8192
             v, s, dt, cores = cpu_baseline(args.population, H, sample)
