@@ -189,7 +189,8 @@ __device__ __forceinline__ void mlp_tmem_chunks(Mlp& m, uint32_t taddr, uint32_t
 }
 
 // evolve/brain.py:56-76 on this lane's staged weights (warp-converged: tcgen05.ld is .sync.aligned)
-__device__ __forceinline__ void brain(Drone& d, uint32_t taddr, const double2* __restrict__ wrow, double neg_beta, bool keep_old) {
+__device__ __forceinline__ void brain(Drone& d, uint32_t taddr, const double2* __restrict__ wrow, double neg_beta, bool keep_old,
+                                      uint32_t (&a)[32]) {
     Mlp m;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -199,8 +200,8 @@ __device__ __forceinline__ void brain(Drone& d, uint32_t taddr, const double2* _
         m.in[9 + i] = d.v[3 + i];
         m.in[12 + i] = d.coin[i];
     }
-    uint32_t a[32], b[32];
-    tmem_ld32(a, taddr);
+    // chunk 0 was requested before the physics of this step (its latency hides behind it)
+    uint32_t b[32];
     tmem_wait_ld(a);
     mlp_tmem_chunks<0>(m, taddr, a, b);
     mlp_smem_tail(m, wrow);
@@ -348,6 +349,8 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
         bool crashed, done;
         do {
             int u;
+            uint32_t w0[32];
+            tmem_ld32(w0, taddr); // first 16 brain weights for this step's MLP, in flight during the physics
             step_rewards_and_coin(p, d, live, time_reward);
             crashed = physics_step<EXTRAS>(p, d, rcp_m, MODE != kPlain ? a_last : nullptr, u) && live;
             d.reward += crashed ? p.reward_crashed : ((live ? u : 0) * p.reward_unstable);
@@ -358,7 +361,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             }
             // next step's trigonometry and this step's brain: independent, interleaved by the scheduler
             trig_update(d);
-            brain(d, taddr, wrow, neg_beta, MODE != kPlain && crashed);
+            brain(d, taddr, wrow, neg_beta, MODE != kPlain && crashed, w0);
             if (MODE == kTrace) {
                 if (live && !crashed) {
 #pragma unroll
