@@ -31,8 +31,12 @@ sys.path.insert(0, ROOT)
 METRIC = "drone-steps/sec (dynamics+brain+reward)"
 UNIT = "drone-steps/s"
 FLOP_PER_STEP = 850.0  # SURVEY.md §8d algorithmic work per drone-step (FMA = 2)
+FP64_INSTR_PER_STEP = 642.0  # executed fp64-pipe instructions per drone-step (ncu source counters, profiles/r01_d_*)
 GENOME_BYTES = 314 * 8
 RECORD_BYTES = 32
+# dram__bytes_read.sum + dram__bytes_write.sum of fly_mlp_f64_kernel for the default workload
+# (65,536 survivors x 2,000 steps), one `ncu --set full` capture: profiles/r01_d_fly_mlp_f64_ncu_full_summary.csv
+NCU_TRAFFIC_DEFAULT_WORKLOAD = 165176576 + 4155136
 
 
 def population(kind, n, seed=2026):
@@ -209,6 +213,7 @@ def main():
 
     D, H = args.drones_per_gpu, args.timesteps
     params = make_params(H)
+    params.refill_batch = int(os.environ.get("LD_REFILL_BATCH", "0"))
     # every rank flies its own shard of the global population [rank*D, (rank+1)*D)
     host_genomes = population(args.population, D * world)[rank * D:(rank + 1) * D]
     pinned = torch.from_numpy(np.ascontiguousarray(host_genomes)).pin_memory()
@@ -328,14 +333,21 @@ def main():
                        "l2": f"inputs larger than L2 ({D * GENOME_BYTES / 1e6:.0f} MB genome matrix per GPU re-read every step)",
                        "parallelism": f"population sharded over {world} GPU(s), no data-path collective; records all-gathered"},
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks_src,
+                         "frac": achieved_gbs / peaks["hbm_gbs"],
+                         "traffic": NCU_TRAFFIC_DEFAULT_WORKLOAD if (D, H, args.population) == (65536, 2000, "survivors") else None,
+                         "algorithmic_bytes": alg_bytes, "peak_source": peaks_src,
                          "kernel": "fly_mlp_f64_kernel", "kernel_ms": kernel_ms,
                          "note": "compute-bound by construction (SURVEY §8d): 2,544 algorithmic bytes per 2,000-step "
-                                 "episode; the binding roofline is the fp64 pipe, see fp64_roofline"},
+                                 "episode; the binding resources are the fp64 pipe and the register-file fill path that streams "
+                                 "each drone's 2.5 KB brain every timestep (DESIGN.md section 4), see fp64_roofline"},
             "fp64_roofline": {"bound": "fp64 FMA pipe (non-tensor)", "achieved": fp64_tf, "peak": tf.value, "unit": "TFLOP/s",
                               "frac": fp64_tf / tf.value, "flop_per_drone_step": FLOP_PER_STEP,
                               "peak_source": "ld_measure_fp64_peak (DFMA-chain microbenchmark, this run)",
-                              "dfma_per_clk_per_sm": per_clk.value},
+                              "dfma_per_clk_per_sm": per_clk.value,
+                              "executed_fp64_instr_per_drone_step": FP64_INSTR_PER_STEP,
+                              "pipe_utilisation": steps_per_launch * FP64_INSTR_PER_STEP / (kernel_ms * 1e-3) / (tf.value * 1e12 / 2.0),
+                              "note": "pipe_utilisation = executed fp64-pipe thread-instructions (ncu: 418 DFMA + 116 DMUL + "
+                                      "83 DADD + 25 DSETP per drone-step, profiles/r01_d_*) / measured DFMA issue peak"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": D * GENOME_BYTES * world,
                     "d2h_bytes_per_step": D * RECORD_BYTES * world, "api": "ld_fly_mlp_f64_host via fly_population_host"},
             "gpu_launches": args.steps * world,

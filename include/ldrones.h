@@ -114,7 +114,7 @@ typedef struct ld_params {
     int32_t timesteps;     /* 2500 default */
     int32_t reward_time;   /* bool */
     int32_t punish_time;   /* bool */
-    int32_t _pad1;
+    int32_t refill_batch;  /* tuning: idle lanes per warp that trigger a queue refill; 0 = library default */
 } ld_params;
 
 /* what fly() leaves on the Drone besides its kinematic state */

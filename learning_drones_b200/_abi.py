@@ -72,7 +72,7 @@ class LdParams(C.Structure):
         ("timesteps", C.c_int32),
         ("reward_time", C.c_int32),
         ("punish_time", C.c_int32),
-        ("_pad1", C.c_int32),
+        ("refill_batch", C.c_int32),
     ]
 
 

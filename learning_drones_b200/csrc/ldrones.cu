@@ -42,7 +42,7 @@ constexpr int kSmemUsed = kCtaThreads * kRowBytes;    // 59392
 // second CTA (e.g. of a concurrent launch on another stream) can never become resident next to us
 constexpr int kSmemBytes = 120 * 1024;
 static_assert(kSmemUsed <= kSmemBytes, "shared-memory rows");
-constexpr int kRefillBatch = 8;                       // idle lanes that trigger a refill
+constexpr int kRefillBatch = 6;                       // idle lanes that trigger a refill
 static_assert((kRowBytes / 16) % 2 == 1, "row stride must be an odd number of 16-B units (bank-conflict-free LDS.128)");
 static_assert(kSmemDoubles % 2 == 0, "double2 staging");
 
@@ -301,7 +301,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
     for (;;) {
         // ---- refill idle lanes from the queue (warp-aggregated fetch, batched) -----------------
         const unsigned idle = __ballot_sync(0xffffffffu, idx < 0);
-        if (more && (__popc(idle) >= kRefillBatch || idle == 0xffffffffu)) {
+        if (more && (__popc(idle) >= (p.refill_batch > 0 ? p.refill_batch : kRefillBatch) || idle == 0xffffffffu)) {
             unsigned long long base = 0;
             const int leader = __ffs(idle) - 1;
             if ((int)lane == leader) base = atomicAdd(queue_head, (unsigned long long)__popc(idle));
