@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ld_step.cuh"
@@ -735,20 +736,21 @@ int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* 
 }
 
 // grow-only device workspace for the *_host entry point (per host thread)
+constexpr int kHostStreams = 8;
 struct Workspace {
     int device = -1;
-    void* genomes[2] = {nullptr, nullptr};
-    void* records[2] = {nullptr, nullptr};
-    void* state[2] = {nullptr, nullptr};
+    void* genomes[kHostStreams] = {};
+    void* records[kHostStreams] = {};
+    void* state[kHostStreams] = {};
     int64_t* counters = nullptr;
     size_t cap_drones = 0;
     bool cap_state = false;
-    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaStream_t streams[kHostStreams] = {};
 };
 thread_local Workspace g_ws;
 
 void ws_release() {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kHostStreams; ++i) {
         if (g_ws.genomes[i]) cudaFree(g_ws.genomes[i]);
         if (g_ws.records[i]) cudaFree(g_ws.records[i]);
         if (g_ws.state[i]) cudaFree(g_ws.state[i]);
@@ -768,13 +770,13 @@ int ws_reserve(size_t chunk, bool want_state) {
     LD_CUDA(cudaGetDevice(&dev));
     if (g_ws.device == dev && g_ws.cap_drones >= chunk && (g_ws.cap_state || !want_state)) return LD_OK;
     ws_release();
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kHostStreams; ++i) {
         LD_CUDA(cudaMalloc(&g_ws.genomes[i], chunk * LD_GENOME_LEN * sizeof(double)));
         LD_CUDA(cudaMalloc(&g_ws.records[i], chunk * sizeof(ld_record)));
         if (want_state) LD_CUDA(cudaMalloc(&g_ws.state[i], chunk * LD_STATE_LEN * sizeof(double)));
         LD_CUDA(cudaStreamCreateWithFlags(&g_ws.streams[i], cudaStreamNonBlocking));
     }
-    LD_CUDA(cudaMalloc((void**)&g_ws.counters, 2 * sizeof(int64_t)));
+    LD_CUDA(cudaMalloc((void**)&g_ws.counters, kHostStreams * sizeof(int64_t)));
     g_ws.device = dev;
     g_ws.cap_drones = chunk;
     g_ws.cap_state = want_state;
@@ -846,16 +848,20 @@ int ld_fly_mlp_f64_host(const ld_params* params, const double* genomes, int64_t 
     if (!genomes || !records) return fail(LD_ERR_INVALID_ARG, "NULL host buffer");
     rc = ensure_device();
     if (rc) return rc;
-    // Chunks are whole waves (every chunk fills the machine) and ramp up 1, 2, 4, 4, ... waves: only
-    // the first, smallest H2D copy is exposed; later copies and the D2H of finished chunks overlap
-    // the kernel of the chunk in between (two buffers, two streams).
+    // Pipeline over kHostStreams streams / buffers.  A chunk is a quarter of a wave (37 of 148 SMs):
+    // kernels of different chunks are resident on disjoint SMs at the same time (a CTA owns its SM's
+    // Tensor Memory), so the machine fills up after four small H2D copies instead of one big one
+    // and every later copy / record read-back hides behind the kernels.  Big populations use
+    // whole-wave chunks (fewer launches).
     const int64_t wave = (int64_t)g_dev.sms * kCtaThreads;
-    const int64_t max_chunk = (n < 4 * wave) ? (n < wave ? n : (n + wave - 1) / wave * wave) : 4 * wave;
-    rc = ws_reserve((size_t)(max_chunk < n ? max_chunk : n), final_state != nullptr);
+    int div = 4;
+    if (const char* e = getenv("LD_HOST_CHUNK_DIV")) div = atoi(e) > 0 ? atoi(e) : 4;
+    int64_t chunk = (n > 16 * wave) ? wave : ((int64_t)((g_dev.sms + div - 1) / div) * kCtaThreads);
+    if (chunk > n) chunk = n;
+    rc = ws_reserve((size_t)chunk, final_state != nullptr);
     if (rc) return rc;
     int b = 0;
-    int64_t chunk = wave;
-    for (int64_t off = 0; off < n; b ^= 1) {
+    for (int64_t off = 0; off < n; b = (b + 1) % kHostStreams) {
         const int64_t m = (n - off < chunk) ? (n - off) : chunk;
         cudaStream_t s = g_ws.streams[b];
         LD_CUDA(cudaMemcpyAsync(g_ws.genomes[b], genomes + off * LD_GENOME_LEN, (size_t)m * LD_GENOME_LEN * sizeof(double),
@@ -868,10 +874,8 @@ int ld_fly_mlp_f64_host(const ld_params* params, const double* genomes, int64_t 
             LD_CUDA(cudaMemcpyAsync(final_state + off * LD_STATE_LEN, g_ws.state[b], (size_t)m * LD_STATE_LEN * sizeof(double),
                                     cudaMemcpyDeviceToHost, s));
         off += m;
-        if (chunk < 4 * wave) chunk *= 2;
     }
-    LD_CUDA(cudaStreamSynchronize(g_ws.streams[0]));
-    LD_CUDA(cudaStreamSynchronize(g_ws.streams[1]));
+    for (int i = 0; i < kHostStreams; ++i) LD_CUDA(cudaStreamSynchronize(g_ws.streams[i]));
     return LD_OK;
 }
 
