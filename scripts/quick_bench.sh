@@ -5,5 +5,5 @@ import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)
     except Exception: print(l[:300]); continue
-    print('value %.4g  ms %.3f  e2e %.4g  fp64frac %.3f  clocks %s' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['fp64_roofline']['frac'], d['clocks']))
+    print('value %.4g  ms %.3f  e2e %.4g  fp64frac %.3f  clocks %s' % (d['value'], d['ms_per_step'], d['e2e']['value'], d["roofline"]["frac"], d['clocks']))
 "
