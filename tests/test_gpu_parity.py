@@ -195,3 +195,27 @@ def test_fly_drop_in(golden):
     assert [r[0] for r in res] == g["reward"].tolist()
     assert [d.flight_time for d in drones] == g["flight_time"].tolist()
     np.testing.assert_allclose([r[1] for r in res], g["real_time"])
+
+
+def test_fly_error_behaviour():
+    """Exceptions of the reference: int(nan) -> ValueError (drone/drone.py:14), timesteps=0 ->
+    UnboundLocalError on `real_time` (flight/__init__.py:99)."""
+    from learning_drones_b200.drone.drone import Drone
+    from learning_drones_b200.flight import fly
+
+    np.random.seed(4)
+    d = Drone(visualize=False, n_servers=0)
+    g = d.controller.genome()
+    g[3] = np.nan  # a NaN weight poisons the thrust, then the whole state
+    d.controller.set_genome(g)
+    with pytest.raises(ValueError):
+        fly(d, timesteps=50)
+    d2 = Drone(visualize=False, n_servers=0)
+    with pytest.raises(UnboundLocalError):
+        fly(d2, timesteps=0)
+    with pytest.raises(NotImplementedError):
+        fly(Drone(visualize=False, n_servers=0), visualize=True)
+    d3 = Drone(visualize=False, n_servers=0)
+    d3.controller.weights = d3.controller.weights[:2]  # wrong brain shape
+    with pytest.raises(ValueError):
+        fly(d3)

@@ -170,3 +170,24 @@ def test_bench_population_matches_fixture_generators(golden):
 
     assert np.array_equal(bench.population("survivors", 65536)[:96], golden("survivors_2000")["genomes"])
     assert np.array_equal(bench.population("random", 65536)[:512], golden("random_2000")["genomes"])
+
+
+def test_trace_dump_in_datahandler_layout(tmp_path, golden):
+    """a fly() trace written in the layout of the reference's DataHandler."""
+    from learning_drones_b200.datahandling import CSV_HEADER, coin_schedule, save_trace
+
+    g = golden("hover_2000")
+    trace = g["trace0"][:300]
+    res = save_trace(str(tmp_path / "run"), trace)
+    assert res.shape == (301, 25) and len(CSV_HEADER.split(",")) == 25
+    for name, cols in (("time", 1), ("thrust_values", 4), ("rotation", 3), ("translation", 3), ("wind", 2), ("pid", 6), ("setpoints", 6)):
+        a = np.load(tmp_path / "run" / f"{name}.npy")
+        assert a.dtype == np.float32 and a.shape == (301, cols) and not a[0].any()
+    assert np.allclose(np.load(tmp_path / "run" / "translation.npy")[1:], trace[:, :3].astype(np.float32))
+    assert open(tmp_path / "run" / "Results.csv").readline().startswith("# Time, Roll, Pitch")
+    sched = coin_schedule(trace)
+    assert (sched == [5.0, 5.0, 10.0]).all()  # the hover drone never reaches the first coin
+    # a path through the first coin switches the set-point to the next one (radius 2 then 1)
+    path = np.zeros((4, 28))
+    path[:, :3] = [[4.9, 4.9, 10.0], [4.9, 4.9, 10.0], [10.0, 7.5, 10.0], [0, 0, 0]]
+    assert coin_schedule(path).tolist() == [[5, 5, 10], [10, 7.5, 10], [10, 7.5, 10], [15, 10, 10]]
