@@ -215,6 +215,24 @@ typedef struct ld_ga_params {
 int ld_ga_step_device(const ld_ga_params* ga, const double* parents, const ld_record* records, int64_t n,
                       double* children, int64_t lo, int64_t hi, void* stream);
 
+/* Same GA step with the parent population SHARDED over the GPUs of one box: rank r owns rows
+ * [r*shard_rows, (r+1)*shard_rows) at peers.shard[r], a pointer valid on THIS device (its own
+ * shard or a peer's buffer mapped over NVLink, e.g. torch symmetric memory buffer_ptrs).  The
+ * kernel loads winner rows straight from the owning GPU's HBM while it applies crossover and
+ * mutation — no all-gather of genomes.  The caller guarantees that no peer overwrites its parent
+ * shard before every rank has finished this step (the next generation's record all-gather is
+ * such a point). */
+#define LD_MAX_PEERS 16
+typedef struct ld_peer_table {
+    const double* shard[LD_MAX_PEERS];
+    int64_t shard_rows; /* rows per rank; n == world * shard_rows, shard_rows even */
+    int32_t world;
+    int32_t _pad;
+} ld_peer_table;
+
+int ld_ga_step_p2p_device(const ld_ga_params* ga, const ld_peer_table* peers, const ld_record* records, int64_t n,
+                          double* children, int64_t lo, int64_t hi, void* stream);
+
 /* ---- population statistics (warp-shuffle reductions) ----------------------
  * stats[0]=sum flight_time (active drone-steps), [1]=max reward, [2]=argmax reward
  * (lowest index wins ties, like np.argmax at evolve/evolution.py:77),

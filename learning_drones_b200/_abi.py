@@ -272,3 +272,26 @@ def make_ga_params(seed: int, generation: int, p_tournament: float = 0.6, p_cros
     g.p_tournament, g.p_crossover = float(p_tournament), float(p_crossover)
     g.mutation_rate, g.mutation_sigma = float(mutation_rate), float(mutation_sigma)
     return g
+
+
+MAX_PEERS = 16
+
+
+class LdPeerTable(C.Structure):
+    _fields_ = [
+        ("shard", C.c_void_p * MAX_PEERS),
+        ("shard_rows", C.c_int64),
+        ("world", C.c_int32),
+        ("_pad", C.c_int32),
+    ]
+
+
+def make_peer_table(shard_ptrs, shard_rows: int) -> LdPeerTable:
+    """shard_ptrs[r]: address, valid on the calling rank's device, of rank r's genome shard."""
+    if not 1 <= len(shard_ptrs) <= MAX_PEERS:
+        raise ValueError(f"1..{MAX_PEERS} peers")
+    t = LdPeerTable()
+    for r, ptr in enumerate(shard_ptrs):
+        t.shard[r] = int(ptr)
+    t.shard_rows, t.world = int(shard_rows), len(shard_ptrs)
+    return t

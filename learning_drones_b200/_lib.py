@@ -5,7 +5,7 @@ There is NO fallback: if the shared library is missing or a call fails, this rai
 import ctypes as C
 import os
 
-from ._abi import LD_ABI_VERSION, LdGaParams, LdParams, LdPidParams, LdRecord
+from ._abi import LD_ABI_VERSION, LdGaParams, LdParams, LdPeerTable, LdPidParams, LdRecord
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libldrones.so")
@@ -26,6 +26,7 @@ EXPORTS = (
     "ld_fly_pid_f64_device",
     "ld_fly_pid_f64_host",
     "ld_ga_step_device",
+    "ld_ga_step_p2p_device",
 )
 
 
@@ -75,6 +76,8 @@ def load():
     L.ld_fly_pid_f64_host.restype = C.c_int
     L.ld_ga_step_device.argtypes = [C.POINTER(LdGaParams), dp, vp, i64, dp, i64, i64, vp]
     L.ld_ga_step_device.restype = C.c_int
+    L.ld_ga_step_p2p_device.argtypes = [C.POINTER(LdGaParams), C.POINTER(LdPeerTable), vp, i64, dp, i64, i64, vp]
+    L.ld_ga_step_p2p_device.restype = C.c_int
     if L.ld_abi_version() != LD_ABI_VERSION:
         raise ImportError(f"libldrones ABI {L.ld_abi_version()} != python binding {LD_ABI_VERSION}; rebuild")
     _lib = L

@@ -523,9 +523,12 @@ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
 
 constexpr uint32_t kStreamSelect = 1, kStreamMutate = 2;
 
+// P2P: the parent population is sharded over the GPUs of the box; `peers.shard[r]` is rank r's shard
+// mapped into this device's address space (NVLink peer memory), rows are fetched with plain loads.
+template <bool P2P>
 __global__ void __launch_bounds__(256)
-ga_step_kernel(const __grid_constant__ ld_ga_params ga, const double* __restrict__ parents, const ld_record* __restrict__ records,
-               long long n, double* __restrict__ children, long long lo, long long hi) {
+ga_step_kernel(const __grid_constant__ ld_ga_params ga, const double* __restrict__ parents, const __grid_constant__ ld_peer_table peers,
+               const ld_record* __restrict__ records, long long n, double* __restrict__ children, long long lo, long long hi) {
     const uint32_t k0 = (uint32_t)ga.seed, k1 = (uint32_t)(ga.seed >> 32), gen = ga.generation;
     const unsigned lane = threadIdx.x & 31u;
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -554,14 +557,23 @@ ga_step_kernel(const __grid_constant__ ld_ga_params ga, const double* __restrict
             // cut position in genome coordinates; "no crossover" = cut at the layer's end
             cut[l] = u53(x.v[0], x.v[1]) < ga.p_crossover ? lo_g + (int)(u53(x.v[2], x.v[3]) * (double)genes) : lo_g + genes;
         }
-        const double* __restrict__ pa = parents + win[0] * LD_GENOME_LEN;
-        const double* __restrict__ pb = parents + win[1] * LD_GENOME_LEN;
+        const double* __restrict__ pa;
+        const double* __restrict__ pb;
+        if (P2P) {
+            const long long ra = win[0] / peers.shard_rows, rb = win[1] / peers.shard_rows;
+            pa = peers.shard[ra] + (win[0] - ra * peers.shard_rows) * LD_GENOME_LEN;
+            pb = peers.shard[rb] + (win[1] - rb * peers.shard_rows) * LD_GENOME_LEN;
+        } else {
+            pa = parents + win[0] * LD_GENOME_LEN;
+            pb = parents + win[1] * LD_GENOME_LEN;
+        }
         double* __restrict__ ca = children + (c - lo) * LD_GENOME_LEN;
         double* __restrict__ cb = children + (c + 1 - lo) * LD_GENOME_LEN;
         for (int g = (int)lane; g < LD_GENOME_LEN; g += 32) { // coalesced 256-B row segments
             const int l = g < kL1 ? 0 : (g < kL1 + kL2 ? 1 : 2);
             const bool swapped = g >= cut[l]; // tail of a crossed layer comes from the other child
-            double wa = __ldg(pa + g), wb = __ldg(pb + g);
+            // peer memory is not covered by the read-only (non-coherent) path's assumptions: plain loads
+            double wa = P2P ? pa[g] : __ldg(pa + g), wb = P2P ? pb[g] : __ldg(pb + g);
             double va = swapped ? wb : wa, vb = swapped ? wa : wb;
 #pragma unroll
             for (int w = 0; w < 2; ++w) {
@@ -953,7 +965,29 @@ int ld_ga_step_device(const ld_ga_params* ga, const double* parents, const ld_re
     long long pairs = (hi - lo) / 2;
     long long blocks = (pairs + 7) / 8;
     if (blocks > 16LL * g_dev.sms) blocks = 16LL * g_dev.sms;
-    ga_step_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*ga, parents, records, n, children, lo, hi);
+    ld_peer_table none;
+    memset(&none, 0, sizeof(none));
+    ga_step_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*ga, parents, none, records, n, children, lo, hi);
+    LD_CUDA(cudaGetLastError());
+    return LD_OK;
+}
+
+int ld_ga_step_p2p_device(const ld_ga_params* ga, const ld_peer_table* peers, const ld_record* records, int64_t n, double* children,
+                          int64_t lo, int64_t hi, void* stream) {
+    if (!ga || !peers || !records || !children) return fail(LD_ERR_INVALID_ARG, "NULL argument");
+    if (peers->world < 1 || peers->world > LD_MAX_PEERS || peers->shard_rows < 2 || (peers->shard_rows & 1) ||
+        peers->shard_rows * peers->world != n)
+        return fail(LD_ERR_INVALID_ARG, "peer table: n must equal world * shard_rows with an even shard_rows");
+    for (int r = 0; r < peers->world; ++r)
+        if (!peers->shard[r]) return fail(LD_ERR_INVALID_ARG, "peer table: NULL shard pointer");
+    if (lo < 0 || hi > n || lo > hi || (lo & 1) || (hi & 1)) return fail(LD_ERR_INVALID_ARG, "children range [lo, hi) must be even-aligned inside [0, n]");
+    if (lo == hi) return LD_OK;
+    int rc = ensure_device();
+    if (rc) return rc;
+    long long pairs = (hi - lo) / 2;
+    long long blocks = (pairs + 7) / 8;
+    if (blocks > 16LL * g_dev.sms) blocks = 16LL * g_dev.sms;
+    ga_step_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*ga, nullptr, *peers, records, n, children, lo, hi);
     LD_CUDA(cudaGetLastError());
     return LD_OK;
 }

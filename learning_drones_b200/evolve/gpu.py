@@ -1,7 +1,13 @@
 """The neuro-evolution loop of the reference's evolve/evolution.py:40-118 with everything
 population-sized on the GPU(s): fitness evaluation (fly), best tracking, selection + crossover +
-mutation (ld_ga_step_device) and elitism.  One process per GPU; the genome matrix is replicated,
-each rank flies and breeds its contiguous shard and the shards are all-gathered (NCCL).
+mutation and elitism.  One process per GPU, each rank flies and breeds its contiguous shard.
+
+Multi-GPU parent fetch, two modes:
+  * p2p (default when torch symmetric memory can be set up): every rank keeps ONLY its shard, in
+    symmetric memory; the GA kernel (ld_ga_step_p2p_device) loads the tournament winners' rows
+    straight out of the owning GPU's HBM over NVLink while it applies crossover and mutation.
+    The only collective per generation is the all-gather of the 32-byte fitness records.
+  * replicated: the genome matrix is replicated and the child shards are all-gathered (NCCL).
 
 Differences from the reference, on purpose: random draws come from the library's counter-based
 Philox stream, not numpy's global MT19937, and there is no jsonpickle dump — use
@@ -12,14 +18,14 @@ import ctypes as C
 import numpy as np
 
 from .. import _lib
-from .._abi import GENOME_LEN, make_ga_params, make_params
+from .._abi import GENOME_LEN, make_ga_params, make_params, make_peer_table
 from ..distributed import allgather_records, shard_bounds
 from ..population import fly_population_device, reduce_records
 
 
 class GpuEvolution:
     def __init__(self, genomes, seed: int = 0, timesteps: int = 2500, mutation_rate: float = 0.05, p_tournament: float = 0.6,
-                 p_crossover: float = 0.05, mutation_sigma: float = 0.3, device=None, **fly_kw):
+                 p_crossover: float = 0.05, mutation_sigma: float = 0.3, device=None, p2p=None, **fly_kw):
         import torch
         import torch.distributed as dist
 
@@ -34,37 +40,90 @@ class GpuEvolution:
         self.n = g.shape[0]
         if self.n % (2 * self.world) != 0:
             raise ValueError("population size must be a multiple of 2 x world size (pair slots, equal shards)")
-        self.population = g.to(self.device, dtype=torch.float64).contiguous().clone()
-        self.next_population = torch.empty_like(self.population)
         self.lo, self.hi = shard_bounds(self.n, self.rank, self.world)
+        self.shard_rows = self.hi - self.lo
         self.params = make_params(timesteps=timesteps, **fly_kw)
         self.seed, self.generation = int(seed), 0
         self.hyper = dict(p_tournament=p_tournament, p_crossover=p_crossover, mutation_rate=mutation_rate, mutation_sigma=mutation_sigma)
         self.global_best_score = None
         self.global_best_genome = torch.empty(GENOME_LEN, dtype=torch.float64, device=self.device)
         self.records = None  # fitness records of the generation flown last (whole population)
+        self.p2p = False
+        if self.world > 1 and p2p is not False:
+            try:
+                self._setup_p2p(g)
+                self.p2p = True
+            except Exception as e:  # symmetric memory not available on this system
+                if p2p is True:
+                    raise
+                self._p2p_error = repr(e)
+        if not self.p2p:
+            self.population = g.to(self.device, dtype=torch.float64).contiguous().clone()
+            self.next_population = torch.empty_like(self.population)
+
+    # -- sharded storage in symmetric memory: peers read parent rows over NVLink --------------------
+    def _setup_p2p(self, g):
+        import torch.distributed._symmetric_memory as symm
+
+        torch = self.torch
+        group = self.dist.group.WORLD
+        self._bufs, self._handles, self._tables = [], [], []
+        for _ in range(2):  # parents / children, swapped every generation
+            t = symm.empty(self.shard_rows, GENOME_LEN, dtype=torch.float64, device=self.device)
+            h = symm.rendezvous(t, group.group_name)
+            self._bufs.append(t)
+            self._handles.append(h)
+            self._tables.append(make_peer_table([int(p) for p in h.buffer_ptrs], self.shard_rows))
+        self._cur = 0
+        self._bufs[0].copy_(g[self.lo:self.hi].to(self.device, dtype=torch.float64))
+        torch.cuda.synchronize(self.device)
+        self.dist.barrier()
+
+    def _row(self, index):
+        """Genome row `index` of the CURRENT population (a peer-memory view in p2p mode)."""
+        if not self.p2p:
+            return self.population[index]
+        owner, local = divmod(int(index), self.shard_rows)
+        if owner == self.rank:
+            return self._bufs[self._cur][local]
+        peer = self._handles[self._cur].get_buffer(owner, (self.shard_rows, GENOME_LEN), self.torch.float64)
+        return peer[local]
+
+    @property
+    def local_population(self):
+        return self._bufs[self._cur] if self.p2p else self.population[self.lo:self.hi]
 
     # -- one generation: evolve/evolution.py:50-107 ------------------------------------------------
     def step(self):
         torch = self.torch
         L = _lib.load()
-        local = self.population[self.lo:self.hi]
-        local_records, _ = fly_population_device(local, self.params)
+        local_records, _ = fly_population_device(self.local_population, self.params)
         self.records = allgather_records(local_records, n_global=self.n) if self.dist else local_records
         stats = reduce_records(self.records)  # np.argmax(scores), evolution.py:77-78
         best_score, best_index = stats["best_reward"], stats["best_index"]
         if self.global_best_score is None or best_score > self.global_best_score:  # :80-83
             self.global_best_score = best_score
-            self.global_best_genome.copy_(self.population[best_index])
+            self.global_best_genome.copy_(self._row(best_index))
         ga = make_ga_params(self.seed, self.generation, **self.hyper)
-        children = self.next_population[self.lo:self.hi]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
-            _lib.check(L.ld_ga_step_device(C.byref(ga), self.population.data_ptr(), self.records.data_ptr(), self.n,
-                                           children.data_ptr(), self.lo, self.hi, torch.cuda.current_stream(self.device).cuda_stream))
-        if self.dist:
-            self.dist.all_gather_into_tensor(self.next_population, children.clone())
-        self.next_population[0].copy_(self.global_best_genome)  # elitism, :105-107
-        self.population, self.next_population = self.next_population, self.population
+            if self.p2p:
+                children = self._bufs[1 - self._cur]
+                _lib.check(L.ld_ga_step_p2p_device(C.byref(ga), C.byref(self._tables[self._cur]), self.records.data_ptr(), self.n,
+                                                   children.data_ptr(), self.lo, self.hi, stream))
+                if self.rank == 0:
+                    children[0].copy_(self.global_best_genome)  # elitism, :105-107
+                # peers may still be reading our parent shard; it is not written again before the next
+                # generation's record all-gather, which every rank enters only after its own GA kernel
+                self._cur = 1 - self._cur
+            else:
+                children = self.next_population[self.lo:self.hi]
+                _lib.check(L.ld_ga_step_device(C.byref(ga), self.population.data_ptr(), self.records.data_ptr(), self.n,
+                                               children.data_ptr(), self.lo, self.hi, stream))
+                if self.dist:
+                    self.dist.all_gather_into_tensor(self.next_population, children.clone())
+                self.next_population[0].copy_(self.global_best_genome)  # elitism, :105-107
+                self.population, self.next_population = self.next_population, self.population
         self.generation += 1
         return dict(generation=self.generation - 1, best_score=best_score, best_index=best_index,
                     global_best_score=self.global_best_score, active_steps=stats["active_steps"], coins=stats["coins"],
@@ -75,3 +134,14 @@ class GpuEvolution:
 
     def best_genome(self) -> np.ndarray:
         return self.global_best_genome.cpu().numpy()
+
+    def gather_population(self) -> np.ndarray:
+        """Whole current population on the host (collective in multi-GPU runs)."""
+        torch = self.torch
+        if not self.dist:
+            return self.population.cpu().numpy()
+        if not self.p2p:
+            return self.population.cpu().numpy()
+        out = torch.empty((self.n, GENOME_LEN), dtype=torch.float64, device=self.device)
+        self.dist.all_gather_into_tensor(out, self._bufs[self._cur].clone())
+        return out.cpu().numpy()
