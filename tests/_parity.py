@@ -30,8 +30,6 @@ SETS = [
 ]
 # fraction of robust drones whose continuous state must agree to STATE_TOL, per fixture
 SET_STATE_FRAC = {"selected_2500": 0.8}
-_unused = [
-]
 
 
 def state_dev(a, b):
