@@ -91,12 +91,14 @@ __device__ __forceinline__ void sincos_fast(double x, double& s, double& c) {
     c = __hiloint2double(chi, __double2loint(cc));
 }
 
-// exp(x) for any non-NaN x (large -> +inf, very negative -> 0); NaN is treated as -760 by the
-// clamp, which is harmless here: a NaN can only come from a drone whose state is already NaN.
+// exp(x) for any x (large -> +inf, very negative -> 0, NaN -> NaN)
 __device__ __forceinline__ double exp_fast(double x) {
     const double magic = kRed[7];
-    // clamp so that k stays within the two-step scaling range; exp is saturated out there anyway
-    const double xc = fmin(fmax(x, -760.0), 760.0);
+    // clamp so that k stays within the two-step scaling range; exp is saturated out there anyway.
+    // Written with compares (not fmin/fmax) so that a NaN stays a NaN, as in the reference where a
+    // NaN thrust poisons the state and int(nan) finally raises (drone/drone.py:14).
+    const double xlo = x < -760.0 ? -760.0 : x;
+    const double xc = xlo > 760.0 ? 760.0 : xlo;
     const double q = fma(xc, kRed[4], magic);
     const int k = __double2loint(q);
     const double j = q - magic;
@@ -116,9 +118,10 @@ __device__ __forceinline__ double exp_fast(double x) {
 __device__ __forceinline__ double sigmoid_fast(double x, double neg_beta) {
     const double d = exp_fast(neg_beta * x) + 1.0;
     // exp overflow: d = +inf -> exactly 0 like the reference (the Newton steps would give NaN)
-    const double dd = fmin(d, 1.7976931348623157e308);
+    const bool overflow = d > 1.7976931348623157e308;
+    const double dd = overflow ? 1.7976931348623157e308 : d; // NaN stays NaN
     const double y = div_by(1.0, dd, recip(dd));
-    return d > 1.7976931348623157e308 ? 0.0 : y;
+    return overflow ? 0.0 : y;
 }
 
 } // namespace ld

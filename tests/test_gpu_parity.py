@@ -33,7 +33,8 @@ def test_kernel_matches_reference_fixture(pop, oracle, golden, name, kw, min_rob
     assert robust.mean() >= min_robust
 
 
-@pytest.mark.parametrize("family,n,H", [("survivors", 4096, 2000), ("random", 4096, 2000), ("random", 20000, 2500)])
+@pytest.mark.parametrize("family,n,H", [("survivors", 4096, 2000), ("random", 4096, 2000), ("random", 20000, 2500),
+                                        ("survivors", 65536, 2000), ("random", 65536, 2000)])  # last two: config 3 at FULL size
 def test_kernel_matches_oracle_subsample(pop, oracle, gen, family, n, H):
     """parity on a subsample of the config-3 populations against the CPU oracle."""
     rng = np.random.default_rng(2026)
@@ -219,3 +220,25 @@ def test_fly_error_behaviour():
     d3.controller.weights = d3.controller.weights[:2]  # wrong brain shape
     with pytest.raises(ValueError):
         fly(d3)
+
+
+def test_config4_size_properties(pop, gen):
+    """Config 4 population size (1,048,576 drones) on one GPU: invariants that need no oracle."""
+    import torch
+
+    rng = np.random.default_rng(4)
+    base = gen.random_brains(8192, rng)
+    big = np.tile(base, (128, 1))  # 1 M drones = 128 copies of 8192 brains
+    p = make_params(400)
+    gt = torch.from_numpy(big).cuda()
+    rec, _ = pop.fly_population_device(gt, p)
+    r = pop.records_to_numpy(rec).reshape(128, 8192)
+    # every copy of a brain gets the identical record, wherever the queue placed it
+    assert all(r[k].tobytes() == r[0].tobytes() for k in range(1, 128))
+    coins = r[0]["coins"].astype(np.int64)
+    expect = (2 * r[0]["flight_time"].astype(np.int64) + 2000 * (coins >= 1) + 1000 * np.maximum(coins - 1, 0)
+              - 3000 * (r[0]["status"] & 1) - r[0]["unstable"] - 100 * np.floor(r[0]["distance_to_coin"]).astype(np.int64))
+    assert r[0]["reward"].tolist() == expect.tolist()
+    stats = pop.reduce_records(rec)
+    assert stats["active_steps"] == 128 * int(r[0]["flight_time"].sum())
+    assert stats["best_reward"] == int(r[0]["reward"].max()) and stats["best_index"] == int(np.argmax(r[0]["reward"]))
