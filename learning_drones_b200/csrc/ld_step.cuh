@@ -54,17 +54,23 @@ __device__ __forceinline__ void trig_finish(Trig& g, double tp, double rc) {
     g.t22 = __double2float_rn(div_by(g.cr, g.cp, rc));
 }
 
-__device__ __forceinline__ void trig_update(Drone& d) {
+// straight-line part: valid for |angle| <= kTrigFastMax (always, in practice)
+__device__ __forceinline__ void trig_fast(Drone& d) {
     Trig& g = d.trig;
-    const double roll = d.x[3], pitch = d.x[4], yaw = d.x[5];
-    sincos_fast(roll, g.sr, g.cr);
-    sincos_fast(pitch, g.sp, g.cp);
-    sincos_fast(yaw, g.sy, g.cy);
+    sincos_fast(d.x[3], g.sr, g.cr);
+    sincos_fast(d.x[4], g.sp, g.cp);
+    sincos_fast(d.x[5], g.sy, g.cy);
     const double rc = recip(g.cp);
     trig_finish(g, div_by(g.sp, g.cp, rc), rc); // np.tan(pitch) = sin/cos to ~2 ulp
-    // |angle| beyond the fast reduction's range (never seen in practice: angles are unwrapped but
-    // episodes end long before): redo everything with CUDA's libm (Payne-Hanek reduction).
-    // One warp-uniform, normally-not-taken branch after the straight-line code.
+}
+
+// |angle| beyond the fast reduction's range (never seen in practice: angles are unwrapped but
+// episodes end long before): redo everything with CUDA's libm (Payne-Hanek reduction).  One
+// warp-uniform, normally-not-taken branch; kept apart from trig_fast so that the straight-line
+// part can share a basic block with the MLP.  Must run before the next physics_step.
+__device__ __forceinline__ void trig_fallback(Drone& d) {
+    Trig& g = d.trig;
+    const double roll = d.x[3], pitch = d.x[4], yaw = d.x[5];
     const bool big = !(fabs(roll) <= kTrigFastMax && fabs(pitch) <= kTrigFastMax && fabs(yaw) <= kTrigFastMax);
     if (__any_sync(0xffffffffu, big)) {
         if (big) {
@@ -74,6 +80,11 @@ __device__ __forceinline__ void trig_update(Drone& d) {
             trig_finish(g, tan(pitch), recip(g.cp));
         }
     }
+}
+
+__device__ __forceinline__ void trig_update(Drone& d) {
+    trig_fast(d);
+    trig_fallback(d);
 }
 
 __device__ __forceinline__ void drone_reset(const ld_params& p, Drone& d) {

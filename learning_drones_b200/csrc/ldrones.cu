@@ -360,9 +360,11 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             if (MODE == kTrace) {
                 if (live) write_state(d, a_last, trace + (size_t)t * LD_STATE_LEN);
             }
-            // next step's trigonometry and this step's brain: independent, interleaved by the scheduler
-            trig_update(d);
+            // next step's trigonometry and this step's brain: independent, one basic block, interleaved
+            // by the scheduler; the (never taken) large-angle fallback branch comes after both
+            trig_fast(d);
             brain(d, taddr, wrow, neg_beta, MODE != kPlain && crashed, w0);
+            trig_fallback(d);
             if (MODE == kTrace) {
                 if (live && !crashed) {
 #pragma unroll
