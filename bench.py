@@ -31,12 +31,12 @@ sys.path.insert(0, ROOT)
 METRIC = "drone-steps/sec (dynamics+brain+reward)"
 UNIT = "drone-steps/s"
 FLOP_PER_STEP = 850.0  # SURVEY.md §8d algorithmic work per drone-step (FMA = 2)
-FP64_INSTR_PER_STEP = 642.0  # executed fp64-pipe instructions per drone-step (ncu source counters, profiles/r01_d_*)
+FP64_INSTR_PER_STEP = 638.0  # executed fp64-pipe instructions per drone-step (ncu source counters, profiles/r01_e_*)
 GENOME_BYTES = 314 * 8
 RECORD_BYTES = 32
 # dram__bytes_read.sum + dram__bytes_write.sum of fly_mlp_f64_kernel for the default workload
-# (65,536 survivors x 2,000 steps), one `ncu --set full` capture: profiles/r01_d_fly_mlp_f64_ncu_full_summary.csv
-NCU_TRAFFIC_DEFAULT_WORKLOAD = 165176576 + 4155136
+# (65,536 survivors x 2,000 steps), one `ncu --set full` capture: profiles/r01_e_fly_mlp_f64_ncu_full_summary.csv
+NCU_TRAFFIC_DEFAULT_WORKLOAD = 164892416 + 5989376
 
 
 def population(kind, n, seed=2026):
@@ -346,7 +346,7 @@ def main():
                          "pipe_utilisation": steps_per_launch * FP64_INSTR_PER_STEP / (kernel_ms * 1e-3) / (tf.value * 1e12 / 2.0),
                          "note": "achieved = active drone-steps per launch x 850 algorithmic flop / kernel time; "
                                  "pipe_utilisation = executed fp64-pipe thread-instructions (ncu: 418 DFMA + 116 DMUL + 83 DADD "
-                                 "+ 25 DSETP per drone-step, profiles/r01_d_*) / measured DFMA issue peak; the co-limiter is "
+                                 "+ 21 DSETP per drone-step, profiles/r01_e_*) / measured DFMA issue peak; the co-limiter is "
                                  "the register-file fill path that streams each drone's 2.5 KB brain every step (DESIGN.md 4)"},
             "hbm_roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved_gbs / peaks["hbm_gbs"], "algorithmic_bytes": alg_bytes,
