@@ -242,3 +242,36 @@ def test_config4_size_properties(pop, gen):
     stats = pop.reduce_records(rec)
     assert stats["active_steps"] == 128 * int(r[0]["flight_time"].sum())
     assert stats["best_reward"] == int(r[0]["reward"].max()) and stats["best_index"] == int(np.argmax(r[0]["reward"]))
+
+
+def test_concurrent_callers(pop, gen):
+    """Host threads and CUDA streams calling the library at the same time: every kernel owns its SMs'
+    Tensor Memory exclusively, so concurrent launches must serialise per SM without deadlock and
+    give the results of a lone call."""
+    import threading
+
+    import torch
+
+    rng = np.random.default_rng(21)
+    genomes = [gen.random_brains(3000 + 500 * i, rng) for i in range(4)]
+    p = make_params(500)
+    alone = [pop.fly_population_host(g, p)[0] for g in genomes]
+    out = [None] * 4
+
+    def work(i):
+        out[i] = pop.fly_population_host(genomes[i], p)[0]
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in threads]
+    [t.join(timeout=120) for t in threads]
+    assert all(not t.is_alive() for t in threads)
+    assert all(out[i].tobytes() == alone[i].tobytes() for i in range(4))
+    # device API on several torch streams at once
+    gts = [torch.from_numpy(g).cuda() for g in genomes]
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    recs = []
+    for g, s in zip(gts, streams):
+        with torch.cuda.stream(s):
+            recs.append(pop.fly_population_device(g, p)[0])
+    torch.cuda.synchronize()
+    assert all(pop.records_to_numpy(r).tobytes() == a.tobytes() for r, a in zip(recs, alone))
