@@ -142,13 +142,27 @@ def cpu_baseline(kind, H, sample, threads=0):
     return steps / dt, steps, dt, (threads or O.max_threads())
 
 
+def workload_config(args, world, active_steps=None):
+    """`config` of the JSON line — identical for our arm and the reference arm."""
+    D, H = args.drones_per_gpu, args.timesteps
+    cfg = {"workload": f"configs[2]: {D}-drone {args.population} population per GPU, {H}-step coin episode, "
+                       "batched fitness eval" + (" + NCCL all-gather of fitness records" if world > 1 else ""),
+           "population": args.population, "timesteps": H, "drones_per_gpu": D, "global_drones": D * world,
+           "nominal_drone_steps_per_step": D * world * H,
+           "l2": f"inputs larger than L2 ({D * GENOME_BYTES / 1e6:.0f} MB genome matrix per GPU re-read every step)",
+           "parallelism": f"population sharded over {world} GPU(s), no data-path collective; records all-gathered"}
+    if active_steps is not None:
+        cfg["active_drone_steps_per_step"] = active_steps
+    return cfg
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import oracle as O
 
     cores = O.max_threads()
-    sample = args.cpu_sample or 8192
+    sample = args.cpu_sample or 32768
     H = args.timesteps
     for _ in range(args.warmup):
         cpu_baseline(args.population, H, min(sample, 512))
@@ -163,8 +177,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"configs[2]: {args.drones_per_gpu}-drone {args.population} population, {H}-step coin episode",
-                   "population": args.population, "timesteps": H, "drones_per_gpu": args.drones_per_gpu},
+        "config": workload_config(args, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} drones x {H} steps per step (first rows of the workload population), "
                                    f"C restatement oracle/ld_oracle.c on {cores} threads; the pure-Python reference "
@@ -184,7 +197,7 @@ def main():
     ap.add_argument("--population", default="survivors", choices=["survivors", "random"])
     ap.add_argument("--drones-per-gpu", type=int, default=65536)
     ap.add_argument("--timesteps", type=int, default=2000)
-    ap.add_argument("--cpu-sample", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="drones in the CPU-baseline sample (default 32768: ~20 CPU-seconds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--generations", type=int, default=5, help="generations of the full GA loop to time (0 = skip)")
     args = ap.parse_args()
@@ -326,12 +339,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"configs[2]: {D}-drone {args.population} population per GPU, {H}-step coin episode, "
-                                   "batched fitness eval" + (" + NCCL all-gather of fitness records" if world > 1 else ""),
-                       "population": args.population, "timesteps": H, "drones_per_gpu": D, "global_drones": D * world,
-                       "active_drone_steps_per_step": active_steps, "nominal_drone_steps_per_step": D * world * H,
-                       "l2": f"inputs larger than L2 ({D * GENOME_BYTES / 1e6:.0f} MB genome matrix per GPU re-read every step)",
-                       "parallelism": f"population sharded over {world} GPU(s), no data-path collective; records all-gathered"},
+            "config": workload_config(args, world, active_steps),
             # the binding roofline of this path is the non-tensor fp64 pipe (arithmetic
             # intensity ~650 flop/B), its peak is measured on the box in this run; the HBM figure the
             # north star also asks for is reported next to it.
@@ -361,7 +369,7 @@ def main():
         if gens is not None:
             line["generations"] = gens
         if not args.no_cpu_baseline and world == 1:
-            sample = args.cpu_sample or 8192
+            sample = args.cpu_sample or 32768
             v, s, dt, cores = cpu_baseline(args.population, H, sample)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{sample} drones x {H} steps ({s} active drone-steps, {dt:.1f} s) of the same "
