@@ -523,7 +523,7 @@ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
     return (double)((((unsigned long long)hi << 32) | lo) >> 11) * 0x1.0p-53;
 }
 
-constexpr uint32_t kStreamSelect = 1, kStreamMutate = 2;
+constexpr uint32_t kStreamSelect = 1, kStreamMutate = 2, kStreamNoise = 3;
 
 // P2P: the parent population is sharded over the GPUs of the box; `peers.shard[r]` is rank r's shard
 // mapped into this device's address space (NVLink peer memory), rows are fetched with plain loads.
@@ -531,6 +531,7 @@ template <bool P2P>
 __global__ void __launch_bounds__(256)
 ga_step_kernel(const __grid_constant__ ld_ga_params ga, const double* __restrict__ parents, const __grid_constant__ ld_peer_table peers,
                const ld_record* __restrict__ records, long long n, double* __restrict__ children, long long lo, long long hi) {
+    __shared__ unsigned short mut_list[8][2 * LD_GENOME_LEN]; // per warp: (gene << 1 | child) of the genes to mutate
     const uint32_t k0 = (uint32_t)ga.seed, k1 = (uint32_t)(ga.seed >> 32), gen = ga.generation;
     const unsigned lane = threadIdx.x & 31u;
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -571,25 +572,58 @@ ga_step_kernel(const __grid_constant__ ld_ga_params ga, const double* __restrict
         }
         double* __restrict__ ca = children + (c - lo) * LD_GENOME_LEN;
         double* __restrict__ cb = children + (c + 1 - lo) * LD_GENOME_LEN;
-        for (int g = (int)lane; g < LD_GENOME_LEN; g += 32) { // coalesced 256-B row segments
-            const int l = g < kL1 ? 0 : (g < kL1 + kL2 ? 1 : 2);
-            const bool swapped = g >= cut[l]; // tail of a crossed layer comes from the other child
-            // peer memory is not covered by the read-only (non-coherent) path's assumptions: plain loads
-            double wa = P2P ? pa[g] : __ldg(pa + g), wb = P2P ? pb[g] : __ldg(pb + g);
-            double va = swapped ? wb : wa, vb = swapped ? wa : wb;
+        // Pass 1 — copy with crossover.  Each lane handles groups of 4 consecutive genes (32 B per row, 16-B
+        // vector accesses; rows are 16-B aligned).  One Philox block per child and group gives the four
+        // Bernoulli(mutation_rate) decisions (32-bit resolution); mutated genes are only LISTED here.
+        constexpr int kGroups = (LD_GENOME_LEN + 3) / 4; // 79, the last group has 2 genes
+        const uint32_t thr = (uint32_t)fmin(ga.mutation_rate * 4294967296.0, 4294967295.0);
+        const bool always = ga.mutation_rate >= 1.0;
+        unsigned short* list = mut_list[threadIdx.x >> 5];
+        int n_mut = 0; // warp-uniform
+        for (int q0 = 0; q0 < kGroups; q0 += 32) {
+            const int q = q0 + (int)lane;
+            const bool have = q < kGroups;
+            const int g0 = 4 * q, cnt = !have ? 0 : ((LD_GENOME_LEN - g0) < 4 ? (LD_GENOME_LEN - g0) : 4); // 4, or 2 for the last group
+            U4 m[2];
+            m[0] = philox4x32_10((uint32_t)c, (uint32_t)q, kStreamMutate, gen, k0, k1);
+            m[1] = philox4x32_10((uint32_t)(c + 1), (uint32_t)q, kStreamMutate, gen, k0, k1);
 #pragma unroll
-            for (int w = 0; w < 2; ++w) {
-                const U4 x = philox4x32_10((uint32_t)(c + w), (uint32_t)g, kStreamMutate, gen, k0, k1);
-                if (u53(x.v[0], x.v[1]) < ga.mutation_rate) {
-                    const double u1 = ((double)x.v[2] + 0.5) * 0x1.0p-32, u2 = ((double)x.v[3] + 0.5) * 0x1.0p-32;
-                    const double z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2); // Box-Muller
-                    if (w == 0) va = va + ga.mutation_sigma * z;
-                    else vb = vb + ga.mutation_sigma * z;
+            for (int h = 0; h < 2; ++h) {
+                if (2 * h < cnt) {
+                    // peer memory is not covered by the read-only (non-coherent) path's assumptions: plain loads there
+                    const double2* qa = reinterpret_cast<const double2*>(pa + g0) + h;
+                    const double2* qb = reinterpret_cast<const double2*>(pb + g0) + h;
+                    const double2 ta = P2P ? *qa : __ldg(qa), tb = P2P ? *qb : __ldg(qb);
+                    const int ga0 = g0 + 2 * h, ga1 = ga0 + 1;
+                    const bool s0 = ga0 >= cut[ga0 < kL1 ? 0 : (ga0 < kL1 + kL2 ? 1 : 2)]; // tail of a crossed layer comes
+                    const bool s1 = ga1 >= cut[ga1 < kL1 ? 0 : (ga1 < kL1 + kL2 ? 1 : 2)]; // from the other child
+                    reinterpret_cast<double2*>(ca + g0)[h] = make_double2(s0 ? tb.x : ta.x, s1 ? tb.y : ta.y);
+                    reinterpret_cast<double2*>(cb + g0)[h] = make_double2(s0 ? ta.x : tb.x, s1 ? ta.y : tb.y);
                 }
             }
-            ca[g] = va;
-            cb[g] = vb;
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool hit = j < cnt && (always || m[w].v[j] < thr);
+                    const unsigned vote = __ballot_sync(0xffffffffu, hit);
+                    if (hit) list[n_mut + __popc(vote & ((1u << lane) - 1u))] = (unsigned short)(((g0 + j) << 1) | w);
+                    n_mut += __popc(vote);
+                }
+            }
         }
+        __syncwarp(); // the children rows and the list written above are visible to the whole warp
+        // Pass 2 — mutation (drone/drone.py:167-172), 32 listed genes at a time: one Philox block per mutated
+        // gene for its Box-Muller N(0, sigma) draw, added to the child gene.
+        for (int i = (int)lane; i < n_mut; i += 32) {
+            const int item = list[i], g = item >> 1, w = item & 1;
+            const U4 x = philox4x32_10((uint32_t)(c + w), (uint32_t)g, kStreamNoise, gen, k0, k1);
+            const double u1 = ((double)x.v[0] + 0.5) * 0x1.0p-32, u2 = ((double)x.v[1] + 0.5) * 0x1.0p-32;
+            const double z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+            double* dst = (w ? cb : ca) + g;
+            *dst = *dst + ga.mutation_sigma * z;
+        }
+        __syncwarp(); // the list is reused by this warp's next pair
     }
 }
 

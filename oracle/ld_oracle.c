@@ -466,7 +466,7 @@ static od_u4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
 
 static double u53(uint32_t hi, uint32_t lo) { return (double)((((uint64_t)hi << 32) | lo) >> 11) * 0x1.0p-53; }
 
-enum { OD_STREAM_SELECT = 1, OD_STREAM_MUTATE = 2 };
+enum { OD_STREAM_SELECT = 1, OD_STREAM_MUTATE = 2, OD_STREAM_NOISE = 3 };
 
 static const int od_layer_off[4] = {0, 160, 270, 314};
 
@@ -504,12 +504,19 @@ int ld_oracle_ga_step(const ld_ga_params* ga, const double* parents, const int64
                 }
             }
         }
-        for (int w = 0; w < 2; ++w) { /* drone.py:167-172 */
+        /* drone.py:167-172 — Bernoulli(rate) per gene from one Philox block per group of 4 genes (32-bit
+         * resolution), a second block per mutated gene for its Box-Muller N(0, sigma) draw */
+        double thr_d = ga->mutation_rate * 4294967296.0;
+        uint32_t thr = thr_d >= 4294967295.0 ? 4294967295u : (uint32_t)thr_d;
+        int always = ga->mutation_rate >= 1.0;
+        for (int w = 0; w < 2; ++w) {
             int nm = 0;
+            od_u4 m = {{0, 0, 0, 0}};
             for (int g = 0; g < LD_GENOME_LEN; ++g) {
-                od_u4 x = philox4x32_10((uint32_t)(c + w), (uint32_t)g, OD_STREAM_MUTATE, gen, k0, k1);
-                if (u53(x.v[0], x.v[1]) < ga->mutation_rate) {
-                    double u1 = ((double)x.v[2] + 0.5) * 0x1.0p-32, u2 = ((double)x.v[3] + 0.5) * 0x1.0p-32;
+                if (g % 4 == 0) m = philox4x32_10((uint32_t)(c + w), (uint32_t)(g / 4), OD_STREAM_MUTATE, gen, k0, k1);
+                if (always || m.v[g % 4] < thr) {
+                    od_u4 x = philox4x32_10((uint32_t)(c + w), (uint32_t)g, OD_STREAM_NOISE, gen, k0, k1);
+                    double u1 = ((double)x.v[0] + 0.5) * 0x1.0p-32, u2 = ((double)x.v[1] + 0.5) * 0x1.0p-32;
                     double z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2); /* Box-Muller */
                     ch[w][g] = ch[w][g] + ga->mutation_sigma * z;
                     ++nm;
