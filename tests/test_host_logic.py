@@ -191,3 +191,34 @@ def test_trace_dump_in_datahandler_layout(tmp_path, golden):
     path = np.zeros((4, 28))
     path[:, :3] = [[4.9, 4.9, 10.0], [4.9, 4.9, 10.0], [10.0, 7.5, 10.0], [0, 0, 0]]
     assert coin_schedule(path).tolist() == [[5, 5, 10], [10, 7.5, 10], [10, 7.5, 10], [15, 10, 10]]
+
+
+def test_abi_argument_validation_without_gpu():
+    """Entry points reject bad arguments with LD_ERR_INVALID_ARG (-1) and a message before touching CUDA."""
+    from learning_drones_b200._abi import LdGaParams, make_ga_params, make_peer_table, make_pid_params
+
+    L = _lib.load()
+    p = make_params(10)
+    assert L.ld_fly_mlp_f64_device(None, None, 0, None, None, None, None) == -1
+    assert b"params" in L.ld_last_error()
+    assert L.ld_fly_mlp_f64_device(C.byref(p), None, -1, None, None, None, None) == -1
+    assert L.ld_fly_mlp_f64_device(C.byref(p), None, 5, None, None, None, None) == -1  # NULL buffers
+    assert L.ld_fly_mlp_f64_device(C.byref(p), 8, 5, 16, None, 32, None) == -1        # misaligned genomes
+    assert b"16-byte" in L.ld_last_error()
+    bad = make_params(10)
+    bad.dt = 0.0
+    assert L.ld_fly_mlp_f64_host(C.byref(bad), None, 1, None, None) == -1
+    assert L.ld_fly_mlp_f64_host(C.byref(p), None, 0, None, None) == 0  # empty population is a no-op
+    q = make_pid_params()
+    q.n_coins = 99
+    assert L.ld_fly_pid_f64_device(C.byref(p), C.byref(q), 16, 4, 16, None, None) == -1
+    ga = make_ga_params(1, 0)
+    assert L.ld_ga_step_device(C.byref(ga), 16, 16, 7, 16, 0, 6, None) == -1   # odd population
+    assert L.ld_ga_step_device(C.byref(ga), 16, 16, 8, 16, 1, 7, None) == -1   # odd shard bounds
+    assert b"even" in L.ld_last_error()
+    t = make_peer_table([4096, 8192], 4)
+    assert L.ld_ga_step_p2p_device(C.byref(ga), C.byref(t), 16, 10, 16, 0, 4, None) == -1  # n != world * shard_rows
+    with pytest.raises(ValueError):
+        make_peer_table([], 4)
+    with pytest.raises(_lib.LdError):
+        _lib.check(-1)
