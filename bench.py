@@ -355,7 +355,7 @@ def main():
                          "note": "achieved = active drone-steps per launch x 850 algorithmic flop / kernel time; "
                                  "pipe_utilisation = executed fp64-pipe thread-instructions (ncu: 418 DFMA + 116 DMUL + 83 DADD "
                                  "+ 21 DSETP per drone-step, profiles/r01_e_*) / measured DFMA issue peak; the co-limiter is "
-                                 "the register-file fill path that streams each drone's 2.5 KB brain every step (DESIGN.md 4)"},
+                                 "dependency latency with one warp per SM sub-partition (brain capacity), DESIGN.md 4"},
             "hbm_roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved_gbs / peaks["hbm_gbs"], "algorithmic_bytes": alg_bytes,
                              "traffic": NCU_TRAFFIC_DEFAULT_WORKLOAD if (D, H, args.population) == (65536, 2000, "survivors") else None,
