@@ -199,6 +199,8 @@ def main():
     ap.add_argument("--timesteps", type=int, default=2000)
     ap.add_argument("--cpu-sample", type=int, default=0, help="drones in the CPU-baseline sample (default 32768: ~20 CPU-seconds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
+                    help="f64 = parity mode (the benchmark); f32 = fast mode, statistical agreement only, never the headline")
     ap.add_argument("--generations", type=int, default=5, help="generations of the full GA loop to time (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -234,8 +236,12 @@ def main():
     records = torch.empty((D, 4), dtype=torch.int64, device=dev)
     counter = torch.empty(1, dtype=torch.int64, device=dev)
 
+    prec = args.precision
+    if prec != "f64":
+        args.generations = 0
+
     def step():
-        ldpop.fly_population_device(genomes, params, records=records, work_counter=counter)
+        ldpop.fly_population_device(genomes, params, records=records, work_counter=counter, precision=prec)
         if world > 1:
             return allgather_records(records, n_global=D * world)  # fitness all-gather for selection (NCCL/NVLink)
         return records
@@ -261,7 +267,7 @@ def main():
     e_all0.record()
     for a, b in ev:
         a.record()
-        ldpop.fly_population_device(genomes, params, records=records, work_counter=counter)
+        ldpop.fly_population_device(genomes, params, records=records, work_counter=counter, precision=prec)
         b.record()
         if world > 1:
             allgather_records(records, n_global=D * world)
@@ -287,11 +293,11 @@ def main():
     out_pinned = torch.empty((D, 4), dtype=torch.int64).pin_memory()
     out_np = out_pinned.numpy().view(RECORD_DTYPE).reshape(-1)
     host_np = pinned.numpy()
-    ldpop.fly_population_host(host_np, params, out=out_np)  # warm (allocates the workspace)
+    ldpop.fly_population_host(host_np, params, out=out_np, precision=prec)  # warm (allocates the workspace)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ldpop.fly_population_host(host_np, params, out=out_np)
+        ldpop.fly_population_host(host_np, params, out=out_np, precision=prec)
         _ = int(out_np["reward"].max())  # the step's result is read on the host
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -338,7 +344,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": prec, "data": "synthetic",
             "config": workload_config(args, world, active_steps),
             # the binding roofline of this path is the non-tensor fp64 pipe (arithmetic
             # intensity ~650 flop/B), its peak is measured on the box in this run; the HBM figure the
@@ -368,6 +374,9 @@ def main():
         }
         if gens is not None:
             line["generations"] = gens
+        if prec != "f64":
+            line["note"] = ("float32 FAST MODE: no parity claim (chaotic dynamics, SURVEY 0.4); the roofline objects refer to the "
+                            "fp64 pipe and do not apply; the benchmark of record is --precision f64")
         if not args.no_cpu_baseline and world == 1:
             sample = args.cpu_sample or 32768
             v, s, dt, cores = cpu_baseline(args.population, H, sample)

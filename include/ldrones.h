@@ -154,6 +154,17 @@ int ld_fly_mlp_f64_device(const ld_params* params, const double* genomes, int64_
 int ld_fly_mlp_f64_host(const ld_params* params, const double* genomes, int64_t n,
                         ld_record* records, double* final_state);
 
+/* fp32 FAST MODE: same call contract and the same fp64 genome matrix / record
+ * layout, but state, brain and arithmetic are float32 on the device.  The dynamics are chaotic:
+ * float32 changes the integer outcome of a large fraction of random drones, so this
+ * mode carries NO parity claim and is compared with the fp64 mode statistically only
+ * (tests/test_gpu_f32.py).  final_state[.][18..23] (previous accelerations) is written as 0. */
+int ld_fly_mlp_f32_device(const ld_params* params, const double* genomes, int64_t n,
+                          ld_record* records, double* final_state,
+                          int64_t* work_counter, void* stream);
+int ld_fly_mlp_f32_host(const ld_params* params, const double* genomes, int64_t n,
+                        ld_record* records, double* final_state);
+
 /* Debug tap: fly ONE drone and dump its state after every
  * measure() call: trace[t][LD_STATE_LEN], t < timesteps; rows after the final
  * step are left untouched. Device pointers. */

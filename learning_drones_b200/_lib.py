@@ -27,6 +27,8 @@ EXPORTS = (
     "ld_fly_pid_f64_host",
     "ld_ga_step_device",
     "ld_ga_step_p2p_device",
+    "ld_fly_mlp_f32_device",
+    "ld_fly_mlp_f32_host",
 )
 
 
@@ -61,6 +63,10 @@ def load():
     L.ld_fly_mlp_f64_device.restype = C.c_int
     L.ld_fly_mlp_f64_host.argtypes = [C.POINTER(LdParams), dp, i64, vp, dp]
     L.ld_fly_mlp_f64_host.restype = C.c_int
+    L.ld_fly_mlp_f32_device.argtypes = [C.POINTER(LdParams), dp, i64, vp, dp, vp, vp]
+    L.ld_fly_mlp_f32_device.restype = C.c_int
+    L.ld_fly_mlp_f32_host.argtypes = [C.POINTER(LdParams), dp, i64, vp, dp]
+    L.ld_fly_mlp_f32_host.restype = C.c_int
     L.ld_fly_mlp_f64_trace_device.argtypes = [C.POINTER(LdParams), dp, vp, dp, vp]
     L.ld_fly_mlp_f64_trace_device.restype = C.c_int
     L.ld_reduce_records_device.argtypes = [vp, i64, vp, vp]

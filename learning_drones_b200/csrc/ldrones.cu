@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "ld_f32.cuh"
 #include "ld_step.cuh"
 
 namespace {
@@ -386,6 +387,181 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
 }
 
+// ---- fp32 fast mode: same episode, float32 state and brain, 8 warps per SM (see ld_f32.cuh) ---------
+constexpr int kSmemBytesF32 = 120 * 1024; // > half of the SM's shared memory: one CTA (one TMEM owner) per SM
+static_assert(ldf::kSmemUsed <= kSmemBytesF32, "fp32 shared-memory rows");
+
+template <int C = 0>
+__device__ __forceinline__ void stage_tmem_f32(uint32_t taddr, bool mine_fresh, const double* __restrict__ row) {
+    if constexpr (C < ldf::kChunks) {
+        uint32_t v[32];
+        tmem_ld32(v, taddr + 32 * C);
+        tmem_wait_ld(v);
+        if (mine_fresh) {
+#pragma unroll
+            for (int e = 0; e < ldf::kChunk; ++e) v[e] = __float_as_uint((float)__ldg(row + stored_to_genome(C * ldf::kChunk + e)));
+        }
+        __syncwarp();
+        tmem_st32(v, taddr + 32 * C);
+        stage_tmem_f32<C + 1>(taddr, mine_fresh, row);
+    }
+}
+
+template <int C>
+__device__ __forceinline__ void mlp_chunks_f32(ldf::MlpF& m, uint32_t taddr, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
+    if constexpr (C + 1 < ldf::kChunks) tmem_ld32(nxt, taddr + 32 * (C + 1));
+    ldf::chunk<C>(m, cur);
+    if constexpr (C + 1 < ldf::kChunks) {
+        tmem_wait_ld(nxt);
+        mlp_chunks_f32<C + 1>(m, taddr, nxt, cur);
+    }
+}
+
+template <bool EXTRAS, bool STATE>
+__global__ void __launch_bounds__(ldf::kThreads, 1)
+fly_mlp_f32_kernel(const __grid_constant__ ld_params p, const double* __restrict__ genomes, long long n,
+                   ld_record* __restrict__ records, double* __restrict__ final_state,
+                   unsigned long long* __restrict__ queue_head) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t tmem_base_slot;
+    float2* wrow = reinterpret_cast<float2*>(smem_raw + (size_t)threadIdx.x * ldf::kRowBytes);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = tmem_base_slot;
+    // warps w and w+4 share the lane quadrant w%4 and take 256 columns each
+    const uint32_t taddr = tmem_base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * 256u;
+
+    const ldf::ParamsF f = ldf::narrow(p);
+    const int time_reward = (p.reward_time ? p.reward_time_passed : 0) - (p.punish_time ? p.reward_time_passed : 0);
+    const int H = p.timesteps;
+    ldf::DroneF d;
+    ldf::reset(p, f, d);
+    long long idx = -1;
+    int t = 0;
+    bool more = true;
+
+    auto publish_f32 = [&]() {
+        const float dist = sqrtf(ldf::dist2(d));
+        long long reward = d.reward;
+        if (isfinite(dist)) reward += (long long)p.reward_coin_distance * (long long)dist;
+        else d.status |= LD_STATUS_NONFINITE;
+        int4 lo, hi;
+        lo.x = (int)(unsigned)(reward & 0xffffffffLL);
+        lo.y = (int)(reward >> 32);
+        lo.z = d.coins;
+        lo.w = d.flight_time;
+        hi.x = d.status;
+        hi.y = d.unstable;
+        hi.z = __double2loint((double)dist);
+        hi.w = __double2hiint((double)dist);
+        int4* out = reinterpret_cast<int4*>(records + idx);
+        out[0] = lo;
+        out[1] = hi;
+        if (STATE && final_state) {
+            double* row = final_state + idx * LD_STATE_LEN;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                row[i] = d.x[i];
+                row[3 + i] = d.v[i];
+                row[6 + i] = d.x[3 + i];
+                row[9 + i] = d.v[3 + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                row[12 + i] = d.acc[i];
+                row[18 + i] = 0.0; // previous acceleration is not kept in the fast mode
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) row[24 + i] = d.thrust[i];
+        }
+    };
+
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, idx < 0);
+        if (more && (__popc(idle) >= (p.refill_batch > 0 ? p.refill_batch : kRefillBatch) || idle == 0xffffffffu)) {
+            unsigned long long base = 0;
+            const int leader = __ffs(idle) - 1;
+            if ((int)lane == leader) base = atomicAdd(queue_head, (unsigned long long)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            const long long mine = (long long)base + __popc(idle & ((1u << lane) - 1u));
+            const bool fresh = idx < 0 && mine < n;
+            const double* __restrict__ row = genomes + (fresh ? mine : 0) * LD_GENOME_LEN;
+            if (fresh) {
+                unsigned touch = 0;
+#pragma unroll
+                for (int i = 0; i < LD_GENOME_LEN; i += 16) touch ^= (unsigned)__double2loint(__ldg(row + i));
+                if (touch == 0x9e3779b9u) wrow[0].x = 0.0f;
+#pragma unroll
+                for (int i = 0; i < ldf::kSmemFloats / 2; ++i)
+                    wrow[i] = make_float2((float)__ldg(row + stored_to_genome(ldf::kTmemFloats + 2 * i)),
+                                          (float)__ldg(row + stored_to_genome(ldf::kTmemFloats + 2 * i + 1)));
+                idx = mine;
+                ldf::reset(p, f, d);
+                t = 0;
+            }
+            __syncwarp();
+            stage_tmem_f32(taddr, fresh, row);
+            tmem_wait_st();
+            more = (long long)base + __popc(idle) < n;
+            ldf::trig(d);
+        }
+        if (__ballot_sync(0xffffffffu, idx >= 0) == 0u) break;
+        if (H <= 0) {
+            if (idx >= 0) {
+                publish_f32();
+                idx = -1;
+            }
+            continue;
+        }
+        const bool live = idx >= 0;
+        bool crashed, done;
+        do {
+            int u;
+            ldf::rewards_and_coin(p, f, d, live, time_reward);
+            crashed = ldf::physics<EXTRAS>(f, d, u) && live;
+            d.reward += crashed ? p.reward_crashed : ((live ? u : 0) * p.reward_unstable);
+            d.unstable += (live && !crashed) ? u : 0;
+            d.status |= crashed ? LD_STATUS_CRASHED : 0;
+            ldf::trig(d);
+            ldf::MlpF m;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                m.in[i] = d.x[i];
+                m.in[3 + i] = d.v[i];
+                m.in[6 + i] = d.x[3 + i];
+                m.in[9 + i] = d.v[3 + i];
+                m.in[12 + i] = d.coin[i];
+            }
+            uint32_t a[32], b[32];
+            tmem_ld32(a, taddr);
+            tmem_wait_ld(a);
+            mlp_chunks_f32<0>(m, taddr, a, b);
+            ldf::smem_tail(m, wrow);
+#pragma unroll
+            for (int j = 0; j < ldf::kOut; ++j) {
+                const float th = __fdividef(1.0f, __expf(f.neg_beta * m.out[j]) + 1.0f); // brain.py:37-39
+                d.thrust[j] = (STATE && crashed) ? d.thrust[j] : th;
+            }
+            t += live ? 1 : 0;
+            done = live && (crashed || t >= H);
+        } while (!__any_sync(0xffffffffu, done));
+        if (done) {
+            publish_f32();
+            idx = -1;
+        }
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+}
+
 // ---- PID controller mode: flight/collect_coins.py:278-364 for a batch of gain sets ---------------
 struct PidCtl {
     double kp, ki, kd, I, prev_e, prev_pv;
@@ -735,6 +911,10 @@ int ensure_device() {
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f64_kernel<true, kState>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f64_kernel<false, kTrace>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f64_kernel<true, kTrace>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    LD_CUDA(cudaFuncSetAttribute(fly_mlp_f32_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesF32));
+    LD_CUDA(cudaFuncSetAttribute(fly_mlp_f32_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesF32));
+    LD_CUDA(cudaFuncSetAttribute(fly_mlp_f32_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesF32));
+    LD_CUDA(cudaFuncSetAttribute(fly_mlp_f32_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesF32));
     g_dev.device = dev;
     g_dev.sms = prop.multiProcessorCount;
     g_dev.attrs_set = true;
@@ -756,11 +936,24 @@ int check_params(const ld_params* p) {
 }
 
 int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* records, double* final_state,
-               int64_t* work_counter, double* trace, cudaStream_t s) {
+               int64_t* work_counter, double* trace, cudaStream_t s, bool f32 = false) {
     int rc = ensure_device();
     if (rc) return rc;
     if (n == 0) return LD_OK;
     LD_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(int64_t), s));
+    if (f32) {
+        long long ctas = (n + ldf::kThreads - 1) / ldf::kThreads;
+        if (ctas > g_dev.sms) ctas = g_dev.sms;
+        auto* head = reinterpret_cast<unsigned long long*>(work_counter);
+        const bool ex = has_extras(p), st = final_state != nullptr;
+#define LD_LAUNCH32(EX, ST) \
+    fly_mlp_f32_kernel<EX, ST><<<(unsigned)ctas, ldf::kThreads, kSmemBytesF32, s>>>(*p, genomes, n, records, final_state, head)
+        if (ex) { if (st) LD_LAUNCH32(true, true); else LD_LAUNCH32(true, false); }
+        else { if (st) LD_LAUNCH32(false, true); else LD_LAUNCH32(false, false); }
+#undef LD_LAUNCH32
+        LD_CUDA(cudaGetLastError());
+        return LD_OK;
+    }
     long long ctas = (n + kCtaThreads - 1) / kCtaThreads;
     if (ctas > g_dev.sms) ctas = g_dev.sms;
     dim3 grid((unsigned)ctas), block(kCtaThreads);
@@ -887,8 +1080,8 @@ int ld_fly_mlp_f64_trace_device(const ld_params* params, const double* genome, l
     return LD_OK;
 }
 
-int ld_fly_mlp_f64_host(const ld_params* params, const double* genomes, int64_t n, ld_record* records,
-                        double* final_state) {
+static int fly_mlp_host_impl(const ld_params* params, const double* genomes, int64_t n, ld_record* records, double* final_state,
+                             bool f32) {
     int rc = check_params(params);
     if (rc) return rc;
     if (n < 0) return fail(LD_ERR_INVALID_ARG, "n < 0");
@@ -901,10 +1094,11 @@ int ld_fly_mlp_f64_host(const ld_params* params, const double* genomes, int64_t 
     // Tensor Memory), so the machine fills up after four small H2D copies instead of one big one
     // and every later copy / record read-back hides behind the kernels.  Big populations use
     // whole-wave chunks (fewer launches).
-    const int64_t wave = (int64_t)g_dev.sms * kCtaThreads;
+    const int64_t cta = f32 ? ldf::kThreads : kCtaThreads;
+    const int64_t wave = (int64_t)g_dev.sms * cta;
     int div = 4;
     if (const char* e = getenv("LD_HOST_CHUNK_DIV")) div = atoi(e) > 0 ? atoi(e) : 4;
-    int64_t chunk = (n > 16 * wave) ? wave : ((int64_t)((g_dev.sms + div - 1) / div) * kCtaThreads);
+    int64_t chunk = (n > 16 * wave) ? wave : ((int64_t)((g_dev.sms + div - 1) / div) * cta);
     if (chunk > n) chunk = n;
     rc = ws_reserve((size_t)chunk, final_state != nullptr);
     if (rc) return rc;
@@ -915,7 +1109,7 @@ int ld_fly_mlp_f64_host(const ld_params* params, const double* genomes, int64_t 
         LD_CUDA(cudaMemcpyAsync(g_ws.genomes[b], genomes + off * LD_GENOME_LEN, (size_t)m * LD_GENOME_LEN * sizeof(double),
                                 cudaMemcpyHostToDevice, s));
         rc = launch_fly(params, (const double*)g_ws.genomes[b], m, (ld_record*)g_ws.records[b],
-                        final_state ? (double*)g_ws.state[b] : nullptr, g_ws.counters + b, nullptr, s);
+                        final_state ? (double*)g_ws.state[b] : nullptr, g_ws.counters + b, nullptr, s, f32);
         if (rc) return rc;
         LD_CUDA(cudaMemcpyAsync(records + off, g_ws.records[b], (size_t)m * sizeof(ld_record), cudaMemcpyDeviceToHost, s));
         if (final_state)
@@ -925,6 +1119,24 @@ int ld_fly_mlp_f64_host(const ld_params* params, const double* genomes, int64_t 
     }
     for (int i = 0; i < kHostStreams; ++i) LD_CUDA(cudaStreamSynchronize(g_ws.streams[i]));
     return LD_OK;
+}
+
+int ld_fly_mlp_f64_host(const ld_params* params, const double* genomes, int64_t n, ld_record* records, double* final_state) {
+    return fly_mlp_host_impl(params, genomes, n, records, final_state, false);
+}
+
+int ld_fly_mlp_f32_host(const ld_params* params, const double* genomes, int64_t n, ld_record* records, double* final_state) {
+    return fly_mlp_host_impl(params, genomes, n, records, final_state, true);
+}
+
+int ld_fly_mlp_f32_device(const ld_params* params, const double* genomes, int64_t n, ld_record* records,
+                          double* final_state, int64_t* work_counter, void* stream) {
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (n < 0) return fail(LD_ERR_INVALID_ARG, "n < 0");
+    if (n > 0 && (!genomes || !records || !work_counter)) return fail(LD_ERR_INVALID_ARG, "NULL device buffer");
+    if (reinterpret_cast<uintptr_t>(records) & 15u) return fail(LD_ERR_INVALID_ARG, "records must be 16-byte aligned");
+    return launch_fly(params, genomes, n, records, final_state, work_counter, nullptr, (cudaStream_t)stream, true);
 }
 
 int ld_reduce_records_device(const ld_record* records, int64_t n, int64_t* stats5, void* stream) {

@@ -22,10 +22,17 @@ def _params(params, kw) -> LdParams:
 
 
 # ---- host buffers in, host buffers out (C-ABI ld_fly_mlp_f64_host) ---------------------------
-def fly_population_host(genomes, params: LdParams = None, want_state: bool = False, out=None, **kw):
+def _entry(L, precision: str, where: str):
+    if precision not in ("f64", "f32"):
+        raise ValueError("precision must be 'f64' (parity mode) or 'f32' (fast mode, statistical agreement only)")
+    return getattr(L, f"ld_fly_mlp_{precision}_{where}")
+
+
+def fly_population_host(genomes, params: LdParams = None, want_state: bool = False, out=None, precision: str = "f64", **kw):
     """genomes: (n, 314) float64 array-like in HOST memory -> (records[n] structured, state|None).
 
     `out` may be a preallocated RECORD_DTYPE array (e.g. backed by pinned memory).
+    precision="f32" selects the float32 fast mode (no parity claim, see include/ldrones.h).
     """
     L = _lib.load()
     p = _params(params, kw)
@@ -38,14 +45,14 @@ def fly_population_host(genomes, params: LdParams = None, want_state: bool = Fal
         raise ValueError("`out` must be a contiguous RECORD_DTYPE array of length n")
     st = np.empty((n, STATE_LEN), dtype=np.float64) if want_state else None
     _lib.check(
-        L.ld_fly_mlp_f64_host(C.byref(p), g.ctypes.data, n, rec.ctypes.data, st.ctypes.data if want_state else None)
+        _entry(L, precision, "host")(C.byref(p), g.ctypes.data, n, rec.ctypes.data, st.ctypes.data if want_state else None)
     )
     return rec, st
 
 
 # ---- device tensors (torch owns the memory) ---------------------------------------------------
 def fly_population_device(genomes, params: LdParams = None, want_state: bool = False, records=None, state=None,
-                          work_counter=None, **kw):
+                          work_counter=None, precision: str = "f64", **kw):
     """genomes: CUDA float64 tensor (n, 314).  Asynchronous on torch's current stream.
 
     Returns (records int64[n][4], state float64[n][28] | None); decode with `records_to_numpy`
@@ -70,7 +77,7 @@ def fly_population_device(genomes, params: LdParams = None, want_state: bool = F
             work_counter = torch.empty(1, dtype=torch.int64, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(
-            L.ld_fly_mlp_f64_device(
+            _entry(L, precision, "device")(
                 C.byref(p),
                 genomes.data_ptr(),
                 n,
