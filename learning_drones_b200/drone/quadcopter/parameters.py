@@ -1,41 +1,41 @@
 """Physical constants and initial conditions of the simulated quadcopter.
 
-Same names and values as the reference's drone/quadcopter/parameters.py:13-52
-(payload table disabled there, `payload_set = None`, parameters.py:13), so
-`from ...parameters import *` call sites keep working.
+Exports the same module-level names, with the same values, as the reference's
+drone/quadcopter/parameters.py:13-52 so that `from ...parameters import *` call sites keep
+working.  The reference's optional payload table (`iom_collection.npy`, parameters.py:54-63) is
+disabled there (`payload_set = None`) and is not reproduced.
 """
 import numpy as np
 
-payload_set = None
+_SCALARS = {
+    "payload_set": None,
+    # geometry and mass [kg, m, kg m^2]
+    "mass_center": 0.200, "mass_motor": 0.050, "radius_motor_center": 0.1,
+    "I_x": 2160e-6, "I_y": 2160e-6, "I_z": 4210e-6,
+    # environment
+    "gravity": 9.81,        # m/s^2
+    "delta_time": 0.05,     # s — unused by fly(); the integrator step is drone.drone.delta_t
+    "coef_force": 5,        # N per unit thrust command
+    "coef_moment": 0.5,     # N
+    "coef_wind": 0.1,       # kg/m
+    "mass_payload": 0, "x_payload": 0, "y_payload": 0,
+    # generic PID constants of the reference module (kp, ti, td and what follows from them)
+    "kp": 1, "ti": 1, "td": 1,
+}
+_SCALARS["ki"] = _SCALARS["kp"] / _SCALARS["ti"]
+_SCALARS["kd"] = _SCALARS["kp"] * _SCALARS["td"]
+_SCALARS["limitRange"] = [0, 1]
 
-# geometry and mass
-mass_center = 0.200  # kg
-mass_motor = 0.050  # kg
-radius_motor_center = 0.1  # m
-I_x = 2160e-6  # kg m^2
-I_y = 2160e-6
-I_z = 4210e-6
+# column vectors with the dtypes the reference creates (integer thrust / angular velocity!)
+_VECTORS = {
+    "initial_thrust": np.zeros((4, 1), dtype=np.int64),
+    "initial_wind_speed": np.zeros((3, 1), dtype=np.float64),
+    "initial_angle": np.zeros((3, 1), dtype=np.int64) * np.pi / 180,
+    "initial_angle_vel": np.zeros((3, 1), dtype=np.int64),
+    "initial_pos": np.array([[0.0], [0.0], [10.0]]),
+    "initial_vel": np.zeros((3, 1), dtype=np.float64),
+}
 
-gravity = 9.81  # m/s^2
-delta_time = 0.05  # s (unused by fly(); the integrator step is drone.drone.delta_t)
-
-coef_force = 5  # N
-coef_moment = 0.5  # N
-coef_wind = 0.1  # kg/m
-mass_payload = 0
-x_payload = 0
-y_payload = 0
-
-kp = 1
-ti = 1
-td = 1
-ki = kp / ti
-kd = kp * td
-limitRange = [0, 1]
-
-initial_thrust = np.array([[0, 0, 0, 0]]).T
-initial_wind_speed = np.array([[0.0, 0.0, 0.0]]).T
-initial_angle = np.array([[0, 0, 0]]).T * np.pi / 180
-initial_angle_vel = np.array([[0, 0, 0]]).T
-initial_pos = np.array([[0.0, 0.0, 10.0]]).T
-initial_vel = np.array([[0.0, 0.0, 0.0]]).T
+globals().update(_SCALARS)
+globals().update(_VECTORS)
+__all__ = ["np", *_SCALARS, *_VECTORS]

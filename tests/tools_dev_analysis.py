@@ -1,7 +1,7 @@
 """GPU-vs-oracle deviation as a function of the oracle's conditioning number (dev tool)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np
 from _parity import conditioning, state_dev
 from learning_drones_b200 import population as pop
