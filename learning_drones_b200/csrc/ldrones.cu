@@ -1096,8 +1096,7 @@ static int fly_mlp_host_impl(const ld_params* params, const double* genomes, int
     // whole-wave chunks (fewer launches).
     const int64_t cta = f32 ? ldf::kThreads : kCtaThreads;
     const int64_t wave = (int64_t)g_dev.sms * cta;
-    int div = 4;
-    if (const char* e = getenv("LD_HOST_CHUNK_DIV")) div = atoi(e) > 0 ? atoi(e) : 4;
+    const int div = 4; // measured on B200 with 8 streams: quarter-wave chunks give the best end-to-end rate
     int64_t chunk = (n > 16 * wave) ? wave : ((int64_t)((g_dev.sms + div - 1) / div) * cta);
     if (chunk > n) chunk = n;
     rc = ws_reserve((size_t)chunk, final_state != nullptr);
