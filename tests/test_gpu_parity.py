@@ -275,3 +275,19 @@ def test_concurrent_callers(pop, gen):
             recs.append(pop.fly_population_device(g, p)[0])
     torch.cuda.synchronize()
     assert all(pop.records_to_numpy(r).tobytes() == a.tobytes() for r, a in zip(recs, alone))
+
+
+def test_large_angle_fallback_path(pop, oracle, gen):
+    """Angles are never wrapped: beyond |x| = 105615 the kernel's fast range reduction hands
+    over to CUDA's libm (warp-uniform fallback branch).  Spin the drones up so that the branch is taken
+    and compare with the oracle (glibc) — a regular, non-chaotic free fall, so tolerances stay tight."""
+    genomes = np.zeros((64, GENOME_LEN))
+    genomes[:, 270 + 10::11] = -50.0  # output biases: all four thrusts ~ 0 => no torque, pure spin + free fall
+    for rate in ([3e6, 0.0, 0.0], [0.0, 0.0, -5e6], [2e6, 1e3, 4e6]):
+        p = make_params(100, initial_angle_vel=rate)
+        rec, st = pop.fly_population_host(genomes, p, want_state=True)
+        ref, rst = oracle.fly_mlp(p, genomes, want_state=True)
+        assert np.abs(rst[:, 6:9]).max() > 1.5e5            # the fallback range was reached
+        assert rec["flight_time"].tolist() == ref["flight_time"].tolist()
+        assert rec["reward"].tolist() == ref["reward"].tolist()
+        np.testing.assert_allclose(st[:, :12], rst[:, :12], rtol=1e-9, atol=1e-9)
