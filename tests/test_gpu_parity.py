@@ -291,3 +291,28 @@ def test_large_angle_fallback_path(pop, oracle, gen):
         assert rec["flight_time"].tolist() == ref["flight_time"].tolist()
         assert rec["reward"].tolist() == ref["reward"].tolist()
         np.testing.assert_allclose(st[:, :12], rst[:, :12], rtol=1e-9, atol=1e-9)
+
+
+def test_saturating_brains_and_nonfinite_status(pop, oracle, gen):
+    """Huge weights drive exp(-0.4 x) into overflow / underflow: thrust must be exactly 0 or 1 like the
+    reference (1/(inf+1) = 0).  NaN weights must surface as LD_STATUS_NONFINITE."""
+    from learning_drones_b200._abi import STATUS_NONFINITE
+
+    rng = np.random.default_rng(23)
+    genomes = gen.random_brains(2000, rng) * rng.choice([1.0, 30.0, 1e3, 1e5], size=(2000, 1))
+    p = make_params(400)
+    rec, st = pop.fly_population_host(genomes, p, want_state=True)
+    ref, rst = oracle.fly_mlp(p, genomes, want_state=True)
+    cond = conditioning(oracle, p, genomes)
+    ok = cond < COND_ROBUST
+    assert ok.mean() > 0.9
+    assert rec["reward"][ok].tolist() == ref["reward"][ok].tolist()
+    assert rec["flight_time"][ok].tolist() == ref["flight_time"][ok].tolist()
+    sat = np.isin(rst[:, 24:28], (0.0, 1.0)).all(axis=1) & ok
+    assert sat.sum() > 100 and np.array_equal(st[sat, 24:28], rst[sat, 24:28])  # exact 0 / 1 thrusts
+    bad = genomes[:8].copy()
+    bad[:, 5] = np.nan
+    rec, _ = pop.fly_population_host(bad, make_params(50))
+    ref, _ = oracle.fly_mlp(make_params(50), bad)
+    assert ((rec["status"] & STATUS_NONFINITE) != 0).all() and ((ref["status"] & STATUS_NONFINITE) != 0).all()
+    assert rec["flight_time"].tolist() == ref["flight_time"].tolist() == [50] * 8  # NaN never crashes (drone.py:150)
