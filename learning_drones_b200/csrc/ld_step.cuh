@@ -68,10 +68,12 @@ __device__ __forceinline__ void trig_fast(Drone& d) {
 // episodes end long before): redo everything with CUDA's libm (Payne-Hanek reduction).  One
 // warp-uniform, normally-not-taken branch; kept apart from trig_fast so that the straight-line
 // part can share a basic block with the MLP.  Must run before the next physics_step.
-__device__ __forceinline__ void trig_fallback(Drone& d) {
+// `live`: lanes without a drone keep stepping a stale (possibly diverged) state; they must not drag
+// the warp into this branch.
+__device__ __forceinline__ void trig_fallback(Drone& d, bool live = true) {
     Trig& g = d.trig;
     const double roll = d.x[3], pitch = d.x[4], yaw = d.x[5];
-    const bool big = !(fabs(roll) <= kTrigFastMax && fabs(pitch) <= kTrigFastMax && fabs(yaw) <= kTrigFastMax);
+    const bool big = live && !(fabs(roll) <= kTrigFastMax && fabs(pitch) <= kTrigFastMax && fabs(yaw) <= kTrigFastMax);
     if (__any_sync(0xffffffffu, big)) {
         if (big) {
             sincos(roll, &g.sr, &g.cr);

@@ -378,6 +378,9 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
         if (done) {
             publish<MODE>(p, d, a_last, idx, records, final_state);
             idx = -1;
+            // the lane keeps stepping (masked) until the next refill: park it in the initial state so that a
+            // wildly tumbling leftover cannot drag the warp into the large-angle fallback branch
+            drone_reset(p, d);
         }
     }
 
