@@ -343,6 +343,31 @@ def main_pid(out_dir, pool):
     print("pid goldens:", [(ps, r["score"], r["steps"]) for ps, r in zip(PID_PARAMSETS, res)], "script(11) =", script_score)
 
 
+def main_large(out_dir, pool, n=8192):
+    """Reference outputs for rows [512, 512+n) of the config-3 random population (seed 2026).  Only the
+    results are stored — the genomes are regenerated from the seed by `random_brains` (guarded by
+    tests/test_oracle_golden.py::test_population_generators_match_fixture)."""
+    rng = np.random.default_rng(2026)
+    survivors(65536, rng)
+    g = random_brains(65536, rng)[512:512 + n]
+    r = run_population(g, 2000, pool)
+    np.savez_compressed(os.path.join(out_dir, "random_2000_large.npz"), first_row=np.int64(512), n=np.int64(n), timesteps=r["timesteps"],
+                        reward=r["reward"], coins=r["coins"], flight_time=r["flight_time"], crashed=r["crashed"],
+                        distance=r["distance"], position=r["state"][:, :3], checksum=np.float64(g.sum()))
+    print("large fixture:", n, "drones; crashed", int(r["crashed"].sum()), "coins", int(r["coins"].sum()))
+
+
+if __name__ == "__main__" and "--large-only" in sys.argv:
+    sys.argv.remove("--large-only")
+    _out = os.path.join(ROOT, "tests", "golden")
+    os.chdir(tempfile.mkdtemp(prefix="ld_golden_"))
+    import multiprocessing as _mp
+
+    _import_reference()
+    main_large(_out, _mp.get_context("fork").Pool(os.cpu_count()))
+    sys.exit(0)
+
+
 if __name__ == "__main__" and "--pid-only" in sys.argv:
     sys.argv.remove("--pid-only")
     _out = os.path.join(ROOT, "tests", "golden")

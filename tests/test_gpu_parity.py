@@ -316,3 +316,24 @@ def test_saturating_brains_and_nonfinite_status(pop, oracle, gen):
     ref, _ = oracle.fly_mlp(make_params(50), bad)
     assert ((rec["status"] & STATUS_NONFINITE) != 0).all() and ((ref["status"] & STATUS_NONFINITE) != 0).all()
     assert rec["flight_time"].tolist() == ref["flight_time"].tolist() == [50] * 8  # NaN never crashes (drone.py:150)
+
+
+def test_kernel_matches_reference_large(pop, oracle, golden):
+    """The CUDA kernel against 8,192 random drones flown by the REAL reference (results-only fixture)."""
+    from test_oracle_golden import _large_fixture
+
+    g, genomes = _large_fixture(golden)
+    p = make_params(int(g["timesteps"]))
+    cond = conditioning(oracle, p, genomes)
+    rec, state = pop.fly_population_host(genomes, p, want_state=True)
+    robust = cond < COND_ROBUST
+    for k in ("reward", "coins", "flight_time"):
+        assert rec[k][robust].tolist() == g[k][robust].tolist()
+    assert ((rec["status"] & 1) != 0)[robust].tolist() == g["crashed"][robust].tolist()
+    dev = np.max(np.abs(state[robust, :3] - g["position"][robust]) / (1 + np.abs(g["position"][robust])), axis=1)
+    assert np.median(dev) < 1e-10 and (dev < 1e-6).mean() > 0.99
+    same = (rec["reward"] == g["reward"]) & (rec["flight_time"] == g["flight_time"])
+    assert same.mean() > 0.995
+    # fitness rank order of the whole generation (north star): identical on the robust drones
+    a, b = rec["reward"][robust], g["reward"][robust]
+    assert np.argsort(-a, kind="stable").tolist() == np.argsort(-b, kind="stable").tolist()

@@ -96,3 +96,33 @@ def test_edge_cases(oracle):
     assert rec["reward"].tolist() == [-700] * 3
     rec, _ = oracle.fly_mlp(make_params(5), np.zeros((0, GENOME_LEN)))
     assert rec.shape == (0,)
+
+
+def _large_fixture(golden):
+    from oracle import gen_golden as G
+
+    g = golden("random_2000_large")
+    rng = np.random.default_rng(2026)
+    G.survivors(65536, rng)
+    lo, n = int(g["first_row"]), int(g["n"])
+    genomes = G.random_brains(65536, rng)[lo:lo + n]
+    assert float(genomes.sum()) == float(g["checksum"])  # the seed reproduces the brains the reference flew
+    return g, genomes
+
+
+def test_oracle_matches_reference_large(oracle, golden):
+    """8,192 random drones flown by the real reference (results-only fixture)."""
+    g, genomes = _large_fixture(golden)
+    p = make_params(int(g["timesteps"]))
+    cond = conditioning(oracle, p, genomes)
+    rec, state = oracle.fly_mlp(p, genomes, want_state=True)
+    robust = cond < 1e-9
+    assert robust.mean() > 0.98
+    for k in ("reward", "coins", "flight_time"):
+        assert rec[k][robust].tolist() == g[k][robust].tolist()
+    assert ((rec["status"] & 1) != 0)[robust].tolist() == g["crashed"][robust].tolist()
+    dev = np.max(np.abs(state[robust, :3] - g["position"][robust]) / (1 + np.abs(g["position"][robust])), axis=1)
+    assert np.median(dev) < 1e-10 and (dev < 1e-6).mean() > 0.99
+    # among ALL drones (chaotic ones included) only a handful may differ
+    same = (rec["reward"] == g["reward"]) & (rec["flight_time"] == g["flight_time"])
+    assert same.mean() > 0.995
