@@ -343,6 +343,46 @@ def main_pid(out_dir, pool):
     print("pid goldens:", [(ps, r["score"], r["steps"]) for ps, r in zip(PID_PARAMSETS, res)], "script(11) =", script_score)
 
 
+def evolution_loop(Drone, fly_generation, util, seed, n_drones=20, n_generations=6, mutation_rate=0.05, p_tournament=0.6,
+                   p_crossover=0.05):
+    """The generation loop of evolve/evolution.py:40-107 (the script itself cannot be imported: it needs
+    jsonpickle and runs under __main__).  `fly_generation(drones)` -> [(score, time, idx), ...]."""
+    from copy import deepcopy
+
+    np.random.seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        drones = [Drone(visualize=False, n_servers=0) for _ in range(n_drones)]
+    global_best_score, global_best_drone, history = -np.inf, None, []
+    for gen in range(n_generations):
+        scores, times = [0] * n_drones, [0] * n_drones
+        for score, flight_time, idx in fly_generation(drones):      # :64-73
+            scores[idx], times[idx] = score, flight_time
+        best_index = int(np.argmax(scores))                          # :77-78
+        if scores[best_index] > global_best_score:                   # :80-83
+            global_best_score = scores[best_index]
+            global_best_drone = deepcopy(drones[best_index])
+        new_population = util.selection_and_crossover(drones, p_tournament, p_crossover)  # :89
+        for d in new_population:                                     # :91-93
+            d.reset()
+            d.mutate(mutation_rate)
+        drones = new_population                                      # :105-107
+        drones[0] = global_best_drone
+        drones[0].reset()
+        history.append(dict(scores=list(scores), times=list(times), best_index=best_index, global_best=global_best_score))
+    return history
+
+
+def main_evolution(out_dir):
+    Drone, fly = _import_reference()
+    with contextlib.redirect_stdout(io.StringIO()):
+        import evolve.util as rutil
+    hist = evolution_loop(Drone, lambda drones: [fly(d, idx=i) for i, d in enumerate(drones)], rutil, seed=12345)
+    np.savez_compressed(os.path.join(out_dir, "evolution_seed12345.npz"),
+                        scores=np.array([h["scores"] for h in hist], dtype=np.int64), times=np.array([h["times"] for h in hist]),
+                        best_index=np.array([h["best_index"] for h in hist]), global_best=np.array([h["global_best"] for h in hist]))
+    print("evolution fixture:", [h["global_best"] for h in hist])
+
+
 def main_large(out_dir, pool, n=8192):
     """Reference outputs for rows [512, 512+n) of the config-3 random population (seed 2026).  Only the
     results are stored — the genomes are regenerated from the seed by `random_brains` (guarded by
@@ -355,6 +395,13 @@ def main_large(out_dir, pool, n=8192):
                         reward=r["reward"], coins=r["coins"], flight_time=r["flight_time"], crashed=r["crashed"],
                         distance=r["distance"], position=r["state"][:, :3], checksum=np.float64(g.sum()))
     print("large fixture:", n, "drones; crashed", int(r["crashed"].sum()), "coins", int(r["coins"].sum()))
+
+
+if __name__ == "__main__" and "--evolution-only" in sys.argv:
+    sys.argv.remove("--evolution-only")
+    os.chdir(tempfile.mkdtemp(prefix="ld_golden_"))
+    main_evolution(os.path.join(ROOT, "tests", "golden"))
+    sys.exit(0)
 
 
 if __name__ == "__main__" and "--large-only" in sys.argv:

@@ -337,3 +337,22 @@ def test_kernel_matches_reference_large(pop, oracle, golden):
     # fitness rank order of the whole generation (north star): identical on the robust drones
     a, b = rec["reward"][robust], g["reward"][robust]
     assert np.argsort(-a, kind="stable").tolist() == np.argsort(-b, kind="stable").tolist()
+
+
+def test_whole_evolution_loop_drop_in(golden):
+    """BASELINE config 2: the generation loop of evolve/evolution.py (seed 12345, 20 drones, 6 generations)
+    with this package's Drone / fly_population / evolve.util in place of the reference's — scores, flight
+    times, best index and global best of EVERY generation must equal what the reference produced
+    (fixture evolution_seed12345.npz: the same loop driven through the reference's own classes)."""
+    from oracle.gen_golden import evolution_loop
+
+    from learning_drones_b200.drone.drone import Drone
+    from learning_drones_b200.evolve import util
+    from learning_drones_b200.flight import fly_population
+
+    g = golden("evolution_seed12345")
+    hist = evolution_loop(Drone, fly_population, util, seed=12345, n_generations=len(g["scores"]))
+    for gen, h in enumerate(hist):
+        assert h["scores"] == g["scores"][gen].tolist(), gen
+        np.testing.assert_allclose(h["times"], g["times"][gen], rtol=0, atol=1e-12)
+        assert h["best_index"] == int(g["best_index"][gen]) and h["global_best"] == int(g["global_best"][gen])
