@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 
 from learning_drones_b200 import _abi, _lib
-from learning_drones_b200._abi import GENOME_LEN, LAYER_SHAPES, LdParams, LdRecord, make_params, sqrt_threshold
+from learning_drones_b200._abi import GENOME_LEN, LAYER_SHAPES, LdParams, LdRecord, make_params, paramset_to_pid_gains, sqrt_threshold
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
@@ -222,3 +222,34 @@ def test_abi_argument_validation_without_gpu():
         make_peer_table([], 4)
     with pytest.raises(_lib.LdError):
         _lib.check(-1)
+
+
+def test_properties_with_hypothesis():
+    """Property tests of the host-side arithmetic helpers."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from learning_drones_b200.distributed import shard_bounds
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.floats(min_value=1e-6, max_value=1e6, allow_nan=False))
+    def threshold(r):
+        thr = sqrt_threshold(r)
+        assert math.sqrt(thr) >= r > math.sqrt(math.nextafter(thr, 0.0))
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(min_value=0, max_value=10**7), st.integers(min_value=1, max_value=64))
+    def shards(n, world):
+        spans = [shard_bounds(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] and 0 <= a[1] - a[0] - (b[1] - b[0]) <= 1 for a, b in zip(spans, spans[1:]))
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.lists(st.floats(min_value=-10, max_value=10, allow_nan=False), min_size=18, max_size=18))
+    def wiring(g18):
+        w = paramset_to_pid_gains(np.array(g18))
+        assert w.shape == (6, 3) and w[2, 1] == g18[4] and w[0, 0] == g18[0] and w[5, 2] == g18[17]
+
+    threshold()
+    shards()
+    wiring()
