@@ -61,6 +61,10 @@ def check_records(rec, state, g, cond, state_frac=None):
             dev = state_dev(state[robust], g["state"][robust])
             assert np.median(dev) < STATE_MEDIAN, np.median(dev)
             assert (dev < STATE_TOL).mean() >= state_frac, (dev < STATE_TOL).mean()
+            # sensor accelerations (current, previous) and the thrust the Drone is left with
+            rest = np.abs(state[robust, 12:28] - g["state"][robust, 12:28]) / (1.0 + np.abs(g["state"][robust, 12:28]))
+            rest = np.where(np.isfinite(rest), rest, 0.0).max(axis=1)
+            assert np.median(rest) < 1e-8 and (rest < 1e-3).mean() >= state_frac, (np.median(rest), (rest < 1e-3).mean())
     # fitness rank order among the robust drones (north star): identical integers => identical ranking
     a, b = rec["reward"][robust], g["reward"][robust]
     assert np.argsort(-a, kind="stable").tolist() == np.argsort(-b, kind="stable").tolist()
