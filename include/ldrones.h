@@ -171,6 +171,15 @@ int ld_fly_mlp_f32_host(const ld_params* params, const double* genomes, int64_t 
 int ld_fly_mlp_f64_trace_device(const ld_params* params, const double* genome,
                                 ld_record* record, double* trace, void* stream);
 
+/* ---- single steps of a Drone, for code that drives the episode loop itself ----------------------
+ * what = 1: Drone.measure(wind_speed)              (drone/drone.py:129-165; wind via ld_params)
+ *           state rows [n][LD_STATE_LEN] are updated in place; flags[i] = {crashed, number of -1 penalties}
+ * what = 2: Drone.translate_input_to_thrust(coin)  (drone/drone.py:83-86 -> evolve/brain.py:56-76)
+ *           state[.][24..27] (thrust) is replaced by the brain's output for coin[n][3]
+ * Host buffers; same device arithmetic as the episode kernel. */
+int ld_drone_step_host(const ld_params* params, int what, const double* genomes, double* state, const double* coin,
+                       int32_t* flags, int64_t n);
+
 /* ---- PID-controlled episode (second controller mode) ------------
  * The main loop of flight/collect_coins.py:278-364 for a batch of PID gain sets: per step
  * score-1, coin test on the current target (+value, next target), exit when all targets are

@@ -29,6 +29,7 @@ EXPORTS = (
     "ld_ga_step_p2p_device",
     "ld_fly_mlp_f32_device",
     "ld_fly_mlp_f32_host",
+    "ld_drone_step_host",
 )
 
 
@@ -67,6 +68,8 @@ def load():
     L.ld_fly_mlp_f32_device.restype = C.c_int
     L.ld_fly_mlp_f32_host.argtypes = [C.POINTER(LdParams), dp, i64, vp, dp]
     L.ld_fly_mlp_f32_host.restype = C.c_int
+    L.ld_drone_step_host.argtypes = [C.POINTER(LdParams), C.c_int, dp, dp, dp, vp, i64]
+    L.ld_drone_step_host.restype = C.c_int
     L.ld_fly_mlp_f64_trace_device.argtypes = [C.POINTER(LdParams), dp, vp, dp, vp]
     L.ld_fly_mlp_f64_trace_device.restype = C.c_int
     L.ld_reduce_records_device.argtypes = [vp, i64, vp, vp]

@@ -806,6 +806,74 @@ ga_step_kernel(const __grid_constant__ ld_ga_params ga, const double* __restrict
     }
 }
 
+// ---- single calls of Drone.measure / Drone.translate_input_to_thrust (drone/drone.py:83-86,129-165) ----
+// For code that steps a Drone by hand instead of calling fly().  One thread per drone, brain read
+// straight from global memory; same device functions as the episode kernel, so stepping by hand
+// reproduces fly() bit for bit.  state rows: pos vel angle angle_vel acc_current acc_last thrust.
+template <int S, int E = 0>
+__device__ __forceinline__ void mlp_global_block(Mlp& m, const double* __restrict__ genome) {
+    if constexpr (E < 16 && S + E < LD_GENOME_LEN) {
+        mlp_mac<S + E>(m, __ldg(genome + stored_to_genome(S + E)));
+        mlp_global_block<S, E + 1>(m, genome);
+    }
+}
+
+template <int S = 0>
+__device__ __forceinline__ void mlp_global(Mlp& m, const double* __restrict__ genome) {
+    if constexpr (S < LD_GENOME_LEN) {
+        mlp_global_block<S>(m, genome);
+        mlp_global<S + 16>(m, genome);
+    }
+}
+
+template <bool EXTRAS>
+__global__ void __launch_bounds__(128)
+drone_step_kernel(const __grid_constant__ ld_params p, int what, const double* __restrict__ genomes, double* __restrict__ state,
+                  const double* __restrict__ coin, int* __restrict__ flags, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool exists = i < n;
+    double* row = state + (exists ? i : 0) * LD_STATE_LEN;
+    Drone d;
+    drone_reset(p, d);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        d.x[k] = row[k];
+        d.v[k] = row[3 + k];
+        d.x[3 + k] = row[6 + k];
+        d.v[3 + k] = row[9 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d.acc[k] = row[12 + k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d.thrust[k] = row[24 + k];
+    if (what == 1) { // Drone.measure(wind_speed)
+        trig_update(d); // warp-converged: every thread of the block gets here
+        double a_last[6];
+        int u;
+        const bool crashed = physics_step<EXTRAS>(p, d, 1.0 / (double)p.m_total32, a_last, u);
+        if (exists) {
+            write_state(d, a_last, row);
+            flags[2 * i] = crashed ? 1 : 0;
+            flags[2 * i + 1] = crashed ? 0 : u; // the unstable rules are skipped on a crash (drone.py:150-154)
+        }
+    } else { // Drone.translate_input_to_thrust(coin_position)
+        Mlp m;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            m.in[k] = d.x[k];
+            m.in[3 + k] = d.v[k];
+            m.in[6 + k] = d.x[3 + k];
+            m.in[9 + k] = d.v[3 + k];
+            m.in[12 + k] = coin[(exists ? i : 0) * 3 + k];
+        }
+        mlp_global(m, genomes + (exists ? i : 0) * LD_GENOME_LEN);
+        if (exists) {
+#pragma unroll
+            for (int k = 0; k < kOut; ++k) row[24 + k] = sigmoid_fast(m.out[k], -p.sigmoid_beta);
+        }
+    }
+}
+
 // ---- accuracy tap for ld_math.cuh (tests/test_gpu_math.py) --------------------------------------
 __global__ void debug_math_kernel(int fn, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ o0,
                                   double* __restrict__ o1, long long n) {
@@ -1239,6 +1307,44 @@ int ld_ga_step_p2p_device(const ld_ga_params* ga, const ld_peer_table* peers, co
     if (blocks > 16LL * g_dev.sms) blocks = 16LL * g_dev.sms;
     ga_step_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*ga, nullptr, *peers, records, n, children, lo, hi);
     LD_CUDA(cudaGetLastError());
+    return LD_OK;
+}
+
+int ld_drone_step_host(const ld_params* params, int what, const double* genomes, double* state, const double* coin, int32_t* flags,
+                       int64_t n) {
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (what != 1 && what != 2) return fail(LD_ERR_INVALID_ARG, "what must be 1 (measure) or 2 (translate_input_to_thrust)");
+    if (n < 0) return fail(LD_ERR_INVALID_ARG, "n < 0");
+    if (n == 0) return LD_OK;
+    if (!state || (what == 1 && !flags) || (what == 2 && (!genomes || !coin))) return fail(LD_ERR_INVALID_ARG, "NULL host buffer");
+    rc = ensure_device();
+    if (rc) return rc;
+    double *d_state = nullptr, *d_gen = nullptr, *d_coin = nullptr;
+    int* d_flags = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_state, (size_t)n * LD_STATE_LEN * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(d_state, state, (size_t)n * LD_STATE_LEN * sizeof(double), cudaMemcpyHostToDevice);
+    if (what == 1) {
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_flags, (size_t)n * 2 * sizeof(int));
+    } else {
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_gen, (size_t)n * LD_GENOME_LEN * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpy(d_gen, genomes, (size_t)n * LD_GENOME_LEN * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_coin, (size_t)n * 3 * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpy(d_coin, coin, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) {
+        const unsigned blocks = (unsigned)((n + 127) / 128);
+        if (has_extras(params)) drone_step_kernel<true><<<blocks, 128>>>(*params, what, d_gen, d_state, d_coin, d_flags, n);
+        else drone_step_kernel<false><<<blocks, 128>>>(*params, what, d_gen, d_state, d_coin, d_flags, n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(state, d_state, (size_t)n * LD_STATE_LEN * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && what == 1) e = cudaMemcpy(flags, d_flags, (size_t)n * 2 * sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(d_state);
+    if (d_flags) cudaFree(d_flags);
+    if (d_gen) cudaFree(d_gen);
+    if (d_coin) cudaFree(d_coin);
+    if (e != cudaSuccess) return fail(LD_ERR_CUDA, "ld_drone_step_host", e);
     return LD_OK;
 }
 

@@ -89,6 +89,58 @@ class Drone:
                     if np.random.random_sample() < mutation_rate:
                         self.controller.weights[i][j][k] += np.random.normal(0.0, 0.3)
 
+    # -- single steps, for code that drives the episode loop itself (reference drone.py:83-86,129-165).
+    #    Both run on the GPU with the episode kernel's device functions (ld_drone_step_host).
+    def _state_row(self):
+        s = np.zeros(STATE_LEN)
+        s[0:3], s[3:6] = self.position.ravel(), self.velocity.ravel()
+        s[6:9], s[9:12] = self.angle.ravel(), self.angle_vel.ravel()
+        s[12:18] = [x.current_acceleration for x in self.sensors]
+        s[18:24] = [x.last_acceleration for x in self.sensors]
+        s[24:28] = np.asarray(self.thrust, dtype=np.float64).ravel()
+        return s
+
+    def _load_state_row(self, s):
+        self.position, self.velocity = s[0:3].reshape(3, 1).copy(), s[3:6].reshape(3, 1).copy()
+        self.angle, self.angle_vel = s[6:9].reshape(3, 1).copy(), s[9:12].reshape(3, 1).copy()
+        self.thrust = s[24:28].reshape(4, 1).copy()
+        pos, vel = np.concatenate([s[0:3], s[6:9]]), np.concatenate([s[3:6], s[9:12]])
+        for i, sensor in enumerate(self.sensors):
+            sensor.previous_pos, sensor.previous_vel = float(pos[i]), float(vel[i])
+            sensor.current_acceleration, sensor.last_acceleration = float(s[12 + i]), float(s[18 + i])
+
+    def measure(self, wind_speed):
+        """One physics + integrator step and the crash / unstable rules; returns True when crashed."""
+        import ctypes as C
+
+        from .. import _lib
+        from .._abi import make_params
+
+        state = self._state_row()[None, :].copy()
+        flags = np.zeros((1, 2), dtype=np.int32)
+        p = make_params(timesteps=1, wind_speed=wind_speed)
+        _lib.check(_lib.load().ld_drone_step_host(C.byref(p), 1, None, state.ctypes.data, None, flags.ctypes.data, 1))
+        self._load_state_row(state[0])
+        if flags[0, 0]:
+            self.reward += REWARD_CRASHED
+            self.crashed = True
+            return True
+        self.reward += REWARD_UNSTABLE * int(flags[0, 1])
+        return False
+
+    def translate_input_to_thrust(self, coin_position):
+        import ctypes as C
+
+        from .. import _lib
+        from .._abi import make_params
+
+        state = self._state_row()[None, :].copy()
+        genome = self.controller.genome()[None, :].copy()
+        coin = np.asarray(coin_position, dtype=np.float64).reshape(1, 3).copy()
+        p = make_params(timesteps=1)
+        _lib.check(_lib.load().ld_drone_step_host(C.byref(p), 2, genome.ctypes.data, state.ctypes.data, coin.ctypes.data, None, 1))
+        self.thrust = state[0, 24:28].reshape(4, 1).copy()
+
     # -- used by flight.fly -------------------------------------------------------------------
     def start_state(self):
         """State an episode starts from: whatever the attributes currently hold, as in the
@@ -104,11 +156,4 @@ class Drone:
         self.crashed = bool(record["status"] & 1)
         self.distance_to_coin = float(record["distance_to_coin"])
         s = np.asarray(state_row, dtype=np.float64).reshape(STATE_LEN)
-        self.position, self.velocity = s[0:3].reshape(3, 1).copy(), s[3:6].reshape(3, 1).copy()
-        self.angle, self.angle_vel = s[6:9].reshape(3, 1).copy(), s[9:12].reshape(3, 1).copy()
-        self.thrust = s[24:28].reshape(4, 1).copy()
-        pos = np.concatenate([s[0:3], s[6:9]])
-        vel = np.concatenate([s[3:6], s[9:12]])
-        for i, sensor in enumerate(self.sensors):
-            sensor.previous_pos, sensor.previous_vel = float(pos[i]), float(vel[i])
-            sensor.current_acceleration, sensor.last_acceleration = float(s[12 + i]), float(s[18 + i])
+        self._load_state_row(s)

@@ -356,3 +356,36 @@ def test_whole_evolution_loop_drop_in(golden):
         assert h["scores"] == g["scores"][gen].tolist(), gen
         np.testing.assert_allclose(h["times"], g["times"][gen], rtol=0, atol=1e-12)
         assert h["best_index"] == int(g["best_index"][gen]) and h["global_best"] == int(g["global_best"][gen])
+
+
+def test_stepping_a_drone_by_hand_equals_fly(golden):
+    """Drone.measure() + Drone.translate_input_to_thrust() driven by the reference's own loop
+    (flight/__init__.py:39-93, restated here) reproduce fly() bit for bit and hit the reference's numbers."""
+    from learning_drones_b200.drone.drone import REWARD_COIN_DISTANCE, REWARD_TIME_PASSED, Drone
+    from learning_drones_b200.drone.quadcopter.parameters import initial_wind_speed
+    from learning_drones_b200.flight import fly
+    from learning_drones_b200.objects.coins import Coin
+
+    g = golden("seed0_single")
+    np.random.seed(0)
+    a, b = Drone(visualize=False, n_servers=0), Drone(visualize=False, n_servers=0)
+    b.controller.set_genome(a.controller.genome())
+    coin = Coin(np.array([[5.0], [5.0], [10.0]]), 2, 2000)
+    for time in range(2500):
+        a.reward += REWARD_TIME_PASSED
+        a.flight_time += 1
+        if coin.is_in_vicinity(a.position):
+            a.reward += coin.value
+            a.coins += 1
+            coin = Coin(coin.position + np.array([[5.0], [2.5], [0.0]]), 1, value=1000)
+        if a.measure(wind_speed=initial_wind_speed):
+            break
+        a.translate_input_to_thrust(coin.position)
+    a.reward += REWARD_COIN_DISTANCE(coin.distance_drone_to_coin(a.position))
+    reward, real_time, _ = fly(b, idx=0)
+    assert (a.reward, a.flight_time, a.crashed, a.coins) == (reward, b.flight_time, b.crashed, b.coins) == (-4077, 170, True, 0)
+    for x, y in ((a.position, b.position), (a.velocity, b.velocity), (a.angle, b.angle), (a.angle_vel, b.angle_vel), (a.thrust, b.thrust)):
+        assert np.array_equal(x, y)  # same device functions => bit-identical
+    assert [s.current_acceleration for s in a.sensors] == [s.current_acceleration for s in b.sensors]
+    assert [s.last_acceleration for s in a.sensors] == [s.last_acceleration for s in b.sensors]
+    np.testing.assert_allclose(a.position.ravel(), g["state"][0, :3], rtol=1e-7)
