@@ -2,9 +2,10 @@
 
 `weights` is the list of per-layer (n_out, n_in + 1) float64 arrays, bias in the LAST column,
 that the reference's GA operators and jsonpickle checkpoints manipulate.  During fly() the
-forward pass runs inside the CUDA episode kernel (csrc/ld_step.cuh `dense`); `feed_forward`
-here is a host-side inspection helper with the reference's semantics and is never called by
-fly()/fly_population().
+forward pass runs inside the CUDA episode kernel (csrc/ldrones.cu `mlp_mac`), and
+`translate_input_to_thrust` of a Drone-shaped brain runs one GPU step; `feed_forward` is a
+host-side inspection helper with the reference's semantics (any layer shapes) that
+fly()/fly_population() never call.
 """
 import numpy as np
 import numpy.random as npr
@@ -68,6 +69,20 @@ class NeuralNetwork:
         return x
 
     def translate_input_to_thrust(self, drone_position, drone_velocity, drone_angle, drone_angle_velocity, coin_position):
-        return self.feed_forward(
-            np.vstack((drone_position, drone_velocity, drone_angle, drone_angle_velocity, coin_position))
-        )
+        """(4, 1) thrust for one state.  Brains of the Drone's shape run on the GPU with the episode
+        kernel's arithmetic (ld_drone_step_host); other layer shapes use the host helper above."""
+        if not self.is_gpu_shape():
+            return self.feed_forward(np.vstack((drone_position, drone_velocity, drone_angle, drone_angle_velocity, coin_position)))
+        import ctypes as C
+
+        from .. import _lib
+        from .._abi import STATE_LEN, make_params
+
+        state = np.zeros((1, STATE_LEN))
+        for lo, v in ((0, drone_position), (3, drone_velocity), (6, drone_angle), (9, drone_angle_velocity)):
+            state[0, lo:lo + 3] = np.asarray(v, dtype=np.float64).ravel()
+        genome = self.genome()[None, :].copy()
+        coin = np.asarray(coin_position, dtype=np.float64).reshape(1, 3).copy()
+        p = make_params(timesteps=1)
+        _lib.check(_lib.load().ld_drone_step_host(C.byref(p), 2, genome.ctypes.data, state.ctypes.data, coin.ctypes.data, None, 1))
+        return state[0, 24:28].reshape(4, 1).copy()

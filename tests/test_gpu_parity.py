@@ -389,3 +389,15 @@ def test_stepping_a_drone_by_hand_equals_fly(golden):
     assert [s.current_acceleration for s in a.sensors] == [s.current_acceleration for s in b.sensors]
     assert [s.last_acceleration for s in a.sensors] == [s.last_acceleration for s in b.sensors]
     np.testing.assert_allclose(a.position.ravel(), g["state"][0, :3], rtol=1e-7)
+
+
+def test_brain_single_call_matches_host_helper():
+    from learning_drones_b200.evolve.brain import NeuralNetwork
+
+    np.random.seed(9)
+    nn = NeuralNetwork(layer_spec={1: 10, 2: 10, 3: 4})
+    args = [np.random.standard_normal((3, 1)) * s for s in (10, 3, 1, 5, 10)]
+    gpu = nn.translate_input_to_thrust(*args)
+    host = nn.feed_forward(np.vstack(args))
+    assert gpu.shape == (4, 1)
+    np.testing.assert_allclose(gpu, host, rtol=1e-12, atol=1e-15)
