@@ -229,6 +229,7 @@ def main():
     D, H = args.drones_per_gpu, args.timesteps
     params = make_params(H)
     params.refill_batch = int(os.environ.get("LD_REFILL_BATCH", "0"))
+    params.slice_steps = int(os.environ.get("LD_SLICE_STEPS", "0"))
     # every rank flies its own shard of the global population [rank*D, (rank+1)*D)
     host_genomes = population(args.population, D * world)[rank * D:(rank + 1) * D]
     pinned = torch.from_numpy(np.ascontiguousarray(host_genomes)).pin_memory()

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define LD_ABI_VERSION 1
+#define LD_ABI_VERSION 2
 
 /* brain shape fixed by drone/drone.py:65 : NeuralNetwork({1:10, 2:10, 3:4}), n_inputs=15 */
 #define LD_N_IN 15
@@ -115,6 +115,12 @@ typedef struct ld_params {
     int32_t reward_time;   /* bool */
     int32_t punish_time;   /* bool */
     int32_t refill_batch;  /* tuning: idle lanes per warp that trigger a queue refill; 0 = library default */
+    int32_t slice_steps;   /* scheduling only, never changes results: when more drones wait than the GPU has
+                              lanes, an fp64 episode is flown in segments of this many steps and the drone goes
+                              back to the queue in between (round robin), so that a population of long-lived
+                              drones ends together instead of in whole-episode waves.  0 = library default,
+                              < 0 = off (every drone keeps its lane until its episode ends) */
+    int32_t reserved0;
 } ld_params;
 
 /* what fly() leaves on the Drone besides its kinematic state */

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libldrones.so")
 SOURCES = [os.path.join(CSRC, "ldrones.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "ld_step.cuh"), os.path.join(ROOT, "include", "ldrones.h")]
+DEPS = SOURCES + [os.path.join(CSRC, h) for h in ("ld_step.cuh", "ld_math.cuh", "ld_f32.cuh")] + [os.path.join(ROOT, "include", "ldrones.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

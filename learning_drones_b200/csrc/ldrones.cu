@@ -3,11 +3,14 @@
 // Episode kernel layout:
 //   * persistent grid, one CTA of 4 warps per SM (one warp per SM sub-partition); one drone per
 //     lane, its whole episode in registers; lanes pull the next drone from a global queue head.
-//   * each lane's brain (314 fp64 weights) must be re-read every timestep and nothing else is: the
-//     kernel is bound by the per-sub-partition register-file fill rate (measured: ~40 B/clk/warp
-//     from shared memory, ~54 B/clk/warp from Tensor Memory).  256 weights per lane therefore sit
-//     in Tensor Memory (all 512 columns of the lane) and are streamed with tcgen05.ld, 58 in the
-//     lane's shared-memory row.
+//   * each lane's brain (314 fp64 weights) must be re-read every timestep and nothing else is
+//     (measured: ~40 B/clk/warp from shared memory, ~54 B/clk/warp from Tensor Memory).  256 weights
+//     per lane therefore sit in Tensor Memory (all 512 columns of the lane) and are streamed with
+//     tcgen05.ld, 58 in the lane's shared-memory row; what binds is the fp64 pipe + dependency
+//     latency of the one warp a sub-partition has room for.
+//   * long episodes are flown in segments: at a segment boundary a drone whose lane is wanted by
+//     a waiting drone is parked in HBM and re-queued (round robin), so a population of survivors
+//     ends together instead of in whole-episode waves (struct Sched).
 //   * HBM traffic per drone-episode: its 2512-B genome row in, a 32-B record (+224-B state) out.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -115,6 +118,76 @@ __device__ __forceinline__ void tmem_st32(const uint32_t (&v)[32], uint32_t tadd
 }
 
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- the work queue of one launch -----------------------------------------------------------------
+// Slots 0..n-1 are the drones themselves (fresh); slot n+i is the i-th drone that was parked at a
+// segment boundary (requeue[i] = drone + 1, written once, 0 = not yet).  Lanes claim slots in order
+// with one atomicAdd on `head`; a lane whose slot is not filled yet polls it every kPollSteps steps
+// and retires when `done` says that every drone has landed.
+constexpr int kParkDoubles = 32; // 29 used: x6 v6 acc6 thrust4 coin3 thr2 + 3 packed int pairs
+constexpr int kPollSteps = 32;
+struct Sched {
+    unsigned long long* head; // claimed slots
+    unsigned long long* tail; // parked drones appended so far              (NULL when cap == 0)
+    unsigned long long* done; // drones whose record has been published      (NULL when cap == 0)
+    int* requeue;             // [cap]
+    double* park;             // [n][kParkDoubles]
+    long long cap;            // 0 = segments off
+    int slice;                // steps per segment, 1 <= slice <= max(timesteps, 1)
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void park_drone(const Drone& d, double* __restrict__ row) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        row[i] = d.x[i];
+        row[6 + i] = d.v[i];
+        row[12 + i] = d.acc[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) row[18 + i] = d.thrust[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) row[22 + i] = d.coin[i];
+    row[25] = d.thr2;
+    row[26] = __hiloint2double(d.coins, d.reward);
+    row[27] = __hiloint2double(d.unstable, d.flight_time);
+    row[28] = __hiloint2double(d.status, d.coin_value);
+}
+
+// L2 loads: another SM wrote the row (and this SM may hold a stale L1 line of an earlier segment)
+__device__ __forceinline__ void unpark_drone(Drone& d, const double* __restrict__ row) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        d.x[i] = __ldcg(row + i);
+        d.v[i] = __ldcg(row + 6 + i);
+        d.acc[i] = __ldcg(row + 12 + i);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d.thrust[i] = __ldcg(row + 18 + i);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) d.coin[i] = __ldcg(row + 22 + i);
+    d.thr2 = __ldcg(row + 25);
+    const double a = __ldcg(row + 26), b = __ldcg(row + 27), c = __ldcg(row + 28);
+    d.reward = __double2loint(a);
+    d.coins = __double2hiint(a);
+    d.flight_time = __double2loint(b);
+    d.unstable = __double2hiint(b);
+    d.coin_value = __double2loint(c);
+    d.status = __double2hiint(c);
+}
 
 __device__ __forceinline__ void write_state(const Drone& d, const double* a_last, double* row) {
 #pragma unroll
@@ -272,7 +345,7 @@ template <bool EXTRAS, int MODE>
 __global__ void __launch_bounds__(kCtaThreads, 1)
 fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict__ genomes, long long n,
                    ld_record* __restrict__ records, double* __restrict__ final_state,
-                   unsigned long long* __restrict__ queue_head, double* __restrict__ trace) {
+                   const __grid_constant__ Sched q, double* __restrict__ trace) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t tmem_base_slot;
     double2* wrow = reinterpret_cast<double2*>(smem_raw + (size_t)threadIdx.x * kRowBytes);
@@ -293,25 +366,52 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
     const double rcp_m = 1.0 / (double)p.m_total32;
     const int time_reward = (p.reward_time ? p.reward_time_passed : 0) - (p.punish_time ? p.reward_time_passed : 0);
     const int H = p.timesteps;
+    const long long n_slots = n + q.cap;
+    const int batch = p.refill_batch > 0 ? p.refill_batch : kRefillBatch;
 
     Drone d;
     drone_reset(p, d);
-    long long idx = -1; // drone this lane is flying; -1 = idle
-    int t = 0;
-    bool more = true; // queue not yet exhausted (warp-uniform)
+    long long idx = -1;  // drone this lane is flying; -1 = none
+    long long slot = -1; // claimed queue slot whose drone is not staged yet; -1 = none
+    int t = 0, t_end = 0;
+    bool more = true; // slots left to claim (warp-uniform)
 
     for (;;) {
-        // ---- refill idle lanes from the queue (warp-aggregated fetch, batched) -----------------
-        const unsigned idle = __ballot_sync(0xffffffffu, idx < 0);
-        if (more && (__popc(idle) >= (p.refill_batch > 0 ? p.refill_batch : kRefillBatch) || idle == 0xffffffffu)) {
+        // ---- claim queue slots for idle lanes (warp-aggregated, batched) ---------------------------
+        const unsigned occupied = __ballot_sync(0xffffffffu, idx >= 0 || slot >= 0);
+        const unsigned idle = ~occupied;
+        if (more && idle != 0u && (__popc(idle) >= batch || occupied == 0u)) {
             unsigned long long base = 0;
             const int leader = __ffs(idle) - 1;
-            if ((int)lane == leader) base = atomicAdd(queue_head, (unsigned long long)__popc(idle));
+            if ((int)lane == leader) base = atomicAdd(q.head, (unsigned long long)__popc(idle));
             base = __shfl_sync(0xffffffffu, base, leader);
             const long long mine = (long long)base + __popc(idle & ((1u << lane) - 1u));
-            const bool fresh = idx < 0 && mine < n;
-            const double* __restrict__ row = genomes + (fresh ? mine : 0) * LD_GENOME_LEN;
-            if (fresh) {
+            if ((idle >> lane) & 1u) slot = mine < n_slots ? mine : -1;
+            more = (long long)base + __popc(idle) < n_slots;
+        }
+        // ---- whose slot is filled? -------------------------------------------------------------------
+        bool ready = false, resume = false, drained = false;
+        long long who = 0;
+        if (slot >= 0) {
+            if (slot < n) {
+                who = slot;
+                ready = true;
+            } else {
+                const int v = ld_acquire(q.requeue + (slot - n));
+                if (v != 0) {
+                    who = v - 1;
+                    ready = resume = true;
+                } else if ((long long)ld_acquire(q.done) >= n) {
+                    slot = -1; // every drone has landed: nothing will ever be parked again
+                    drained = true;
+                }
+            }
+        }
+        if (__any_sync(0xffffffffu, drained)) more = false;
+        // ---- stage the brains of the lanes that got a drone ------------------------------------------
+        if (__any_sync(0xffffffffu, ready)) {
+            const double* __restrict__ row = genomes + who * LD_GENOME_LEN;
+            if (ready) {
                 // pull the 2512-B row into L1 with 20 independent loads; the gathers below then hit
                 unsigned touch = 0;
 #pragma unroll
@@ -324,29 +424,44 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
                     w.y = __ldg(row + stored_to_genome(kTmemDoubles + 2 * i + 1));
                     wrow[i] = w;
                 }
-                idx = mine;
-                drone_reset(p, d);
-                t = 0;
+                idx = who;
+                slot = -1;
+                if (resume) unpark_drone(d, q.park + who * kParkDoubles);
+                else drone_reset(p, d);
+                t = d.flight_time;
+                t_end = min(H, t + q.slice);
             }
             __syncwarp();
-            stage_tmem(taddr, fresh, row);
+            stage_tmem(taddr, ready, row);
             tmem_wait_st();
-            more = (long long)base + __popc(idle) < n;
             trig_update(d); // warp-converged; recomputing it for lanes in flight is idempotent
         }
-        if (__ballot_sync(0xffffffffu, idx >= 0) == 0u) break;
+        const unsigned flying = __ballot_sync(0xffffffffu, idx >= 0);
+        if (flying == 0u) {
+            const unsigned pending = __ballot_sync(0xffffffffu, slot >= 0);
+            if (pending == 0u && !more) break;
+            if (pending != 0u) __nanosleep(500); // wait for a drone to be parked (or for the last one to land)
+            continue;
+        }
 
         if (H <= 0) { // fly(timesteps=0): the loop body never runs (warp-uniform, cold)
             if (idx >= 0) {
                 const double zeros[6] = {0, 0, 0, 0, 0, 0};
                 publish<MODE>(p, d, zeros, idx, records, final_state);
+                if (q.cap) atomicAdd(q.done, 1ull);
                 idx = -1;
             }
             continue;
         }
-        // ---- hot loop: timesteps of flight/__init__.py:39-93 until some lane's episode ends ---------
-        // `live` cannot change inside: lanes only leave (publish) or join (refill) outside of it.
+        // ---- hot loop: timesteps of flight/__init__.py:39-93 until some lane's segment ends ---------
+        // `live` cannot change inside: lanes only leave (publish / park) or join (stage) outside of it.
+        // Lanes that wait for their slot count kPollSteps steps and then have it looked at again.
         const bool live = idx >= 0;
+        const bool counting = live || slot >= 0;
+        if (!live) {
+            t = 0;
+            t_end = kPollSteps;
+        }
         double a_last[6];
         bool crashed, done;
         do {
@@ -372,15 +487,33 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
                     for (int i = 0; i < 4; ++i) trace[(size_t)t * LD_STATE_LEN + 24 + i] = d.thrust[i];
                 }
             }
-            t += live ? 1 : 0;
-            done = live && (crashed || t >= H);
+            t += counting ? 1 : 0;
+            done = counting && (crashed || t >= t_end);
         } while (!__any_sync(0xffffffffu, done));
-        if (done) {
-            publish<MODE>(p, d, a_last, idx, records, final_state);
-            idx = -1;
-            // the lane keeps stepping (masked) until the next refill: park it in the initial state so that a
-            // wildly tumbling leftover cannot drag the warp into the large-angle fallback branch
-            drone_reset(p, d);
+        if (done && live) {
+            bool leave = true;
+            if (crashed || t >= H) {
+                publish<MODE>(p, d, a_last, idx, records, final_state);
+                if (q.cap) atomicAdd(q.done, 1ull);
+            } else {
+                // segment boundary: give the lane up only if some drone is waiting for one
+                const unsigned long long produced = (unsigned long long)n + (q.cap ? *(volatile unsigned long long*)q.tail : 0ull);
+                if (q.cap && *(volatile unsigned long long*)q.head < produced) {
+                    park_drone(d, q.park + idx * kParkDoubles);
+                    __threadfence();
+                    const unsigned long long at = atomicAdd(q.tail, 1ull);
+                    st_release(q.requeue + at, (int)idx + 1);
+                } else {
+                    t_end = min(H, t + q.slice);
+                    leave = false;
+                }
+            }
+            if (leave) {
+                idx = -1;
+                // the lane keeps stepping (masked) until it gets its next drone: park it in the initial state so
+                // that a wildly tumbling leftover cannot drag the warp into the large-angle fallback branch
+                drone_reset(p, d);
+            }
         }
     }
 
@@ -986,6 +1119,12 @@ int ensure_device() {
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f32_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesF32));
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f32_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesF32));
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f32_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesF32));
+    // the segment queue / parking area of every launch comes from the device's default stream-ordered pool:
+    // let it keep freed blocks instead of returning them to the driver at every synchronisation
+    cudaMemPool_t pool;
+    LD_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long keep = ~0ull;
+    LD_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     g_dev.device = dev;
     g_dev.sms = prop.multiProcessorCount;
     g_dev.attrs_set = true;
@@ -1004,6 +1143,31 @@ int check_params(const ld_params* p) {
     if (!(p->dt > 0.0)) return fail(LD_ERR_INVALID_ARG, "params.dt must be > 0");
     if (!(p->m_total32 > 0.0f)) return fail(LD_ERR_INVALID_ARG, "params.m_total32 must be > 0");
     return LD_OK;
+}
+
+// ld_params.slice_steps == 0: pick the number of segments per episode that wastes the least if every drone
+// flies the whole episode (the case segments exist for).  With W = drones / lanes, q segments turn W waves
+// of H steps into ceil(q W) waves of H/q steps; every extra segment costs one re-staging of the brain
+// (~17 steps, measured on B200).  A population whose waves already divide evenly stays unsegmented.
+int auto_slice(long long n, long long lanes, int H) {
+    constexpr int kMinSlice = 125;
+    constexpr double kRestageSteps = 17.0;
+    if (n <= lanes || H < 2 * kMinSlice) return H;
+    const double W = (double)n / (double)lanes;
+    int best_q = 1;
+    double best = 1e300;
+    for (int q = 1; q <= 8; ++q) {
+        if (q > 1 && (H + q - 1) / q < kMinSlice) break;
+        const double waves = q * W;
+        double full = (double)(long long)waves;
+        if (full < waves - 1e-9) full += 1.0;
+        const double cost = full / waves * (1.0 + kRestageSteps * (q - 1) / (double)H);
+        if (cost < best * 0.995) {
+            best = cost;
+            best_q = q;
+        }
+    }
+    return (H + best_q - 1) / best_q;
 }
 
 int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* records, double* final_state,
@@ -1028,10 +1192,30 @@ int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* 
     long long ctas = (n + kCtaThreads - 1) / kCtaThreads;
     if (ctas > g_dev.sms) ctas = g_dev.sms;
     dim3 grid((unsigned)ctas), block(kCtaThreads);
-    auto* head = reinterpret_cast<unsigned long long*>(work_counter);
     const bool ex = has_extras(p);
+    const int H = p->timesteps;
+    // Episode segments (ld_params.slice_steps): only when drones outnumber the lanes, otherwise nobody ever
+    // waits for a lane.  Queue + parking area come from the stream-ordered pool and go back after the kernel.
+    Sched q;
+    memset(&q, 0, sizeof(q));
+    q.head = reinterpret_cast<unsigned long long*>(work_counter);
+    q.slice = H > 1 ? H : 1;
+    const int slice = p->slice_steps == 0 ? auto_slice(n, ctas * kCtaThreads, H) : p->slice_steps;
+    void* scratch = nullptr;
+    if (!trace && slice > 0 && slice < H && n > ctas * kCtaThreads && n < 0x7fffffffLL) {
+        const long long segments = ((long long)H + slice - 1) / slice;
+        q.cap = (segments - 1) * n;
+        q.slice = slice;
+        const size_t queue_bytes = (16 + (size_t)q.cap * sizeof(int) + 255) & ~(size_t)255;
+        LD_CUDA(cudaMallocAsync(&scratch, queue_bytes + (size_t)n * kParkDoubles * sizeof(double), s));
+        LD_CUDA(cudaMemsetAsync(scratch, 0, queue_bytes, s));
+        q.tail = reinterpret_cast<unsigned long long*>(scratch);
+        q.done = q.tail + 1;
+        q.requeue = reinterpret_cast<int*>(q.tail + 2);
+        q.park = reinterpret_cast<double*>(static_cast<char*>(scratch) + queue_bytes);
+    }
 #define LD_LAUNCH(EX, MD) \
-    fly_mlp_f64_kernel<EX, MD><<<grid, block, kSmemBytes, s>>>(*p, genomes, n, records, final_state, head, trace)
+    fly_mlp_f64_kernel<EX, MD><<<grid, block, kSmemBytes, s>>>(*p, genomes, n, records, final_state, q, trace)
     const int mode = trace ? kTrace : (final_state ? kState : kPlain);
     if (ex) {
         if (mode == kTrace) LD_LAUNCH(true, kTrace);
@@ -1043,7 +1227,9 @@ int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* 
         else LD_LAUNCH(false, kPlain);
     }
 #undef LD_LAUNCH
-    LD_CUDA(cudaGetLastError());
+    cudaError_t launched = cudaGetLastError();
+    if (scratch) LD_CUDA(cudaFreeAsync(scratch, s));
+    if (launched != cudaSuccess) return fail(LD_ERR_CUDA, "fly_mlp_f64_kernel launch", launched);
     return LD_OK;
 }
 
@@ -1348,7 +1534,12 @@ int ld_drone_step_host(const ld_params* params, int what, const double* genomes,
     return LD_OK;
 }
 
-void ld_release_workspace(void) { ws_release(); }
+void ld_release_workspace(void) {
+    ws_release();
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+}
 
 int ld_debug_math_device(int fn, const double* x, const double* y, double* out0, double* out1, int64_t n, void* stream) {
     if (fn < 0 || fn > 3 || n < 0 || (n > 0 && (!x || !out0))) return fail(LD_ERR_INVALID_ARG, "bad arguments");
