@@ -134,7 +134,23 @@ struct Sched {
     double* park;             // [n][kParkDoubles]
     long long cap;            // 0 = segments off
     int slice;                // steps per segment, 1 <= slice <= max(timesteps, 1)
+    // host-buffer entry point: genome rows [0, *arrived) are in HBM, the copy engine raises the count
+    // after every chunk while the kernel is already flying the first ones (NULL = everything is there)
+    const unsigned long long* arrived;
+    int* error;               // set to 1 if a lane gave up waiting (kWaitLimitNs); may be NULL
 };
+constexpr unsigned long long kWaitLimitNs = 20ull * 1000 * 1000 * 1000;
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
@@ -326,7 +342,7 @@ __device__ __forceinline__ void stage_tmem(uint32_t taddr, bool mine_fresh, cons
         if (mine_fresh) {
 #pragma unroll
             for (int e = 0; e < kChunk; ++e) {
-                const double w = __ldg(row + stored_to_genome(C * kChunk + e));
+                const double w = __ldca(row + stored_to_genome(C * kChunk + e));
                 v[2 * e] = (uint32_t)__double2loint(w);
                 v[2 * e + 1] = (uint32_t)__double2hiint(w);
             }
@@ -369,6 +385,8 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
     const long long n_slots = n + q.cap;
     const int batch = p.refill_batch > 0 ? p.refill_batch : kRefillBatch;
 
+    const unsigned long long t_start = globaltimer_ns();
+
     Drone d;
     drone_reset(p, d);
     long long idx = -1;  // drone this lane is flying; -1 = none
@@ -394,8 +412,10 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
         long long who = 0;
         if (slot >= 0) {
             if (slot < n) {
+                // plain (coherent) loads of the row after this acquire see what the copy engine wrote before
+                // it raised the count
                 who = slot;
-                ready = true;
+                ready = q.arrived == nullptr || slot < (long long)ld_acquire_sys(q.arrived);
             } else {
                 const int v = ld_acquire(q.requeue + (slot - n));
                 if (v != 0) {
@@ -415,13 +435,13 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
                 // pull the 2512-B row into L1 with 20 independent loads; the gathers below then hit
                 unsigned touch = 0;
 #pragma unroll
-                for (int i = 0; i < LD_GENOME_LEN; i += 16) touch ^= (unsigned)__double2loint(__ldg(row + i));
+                for (int i = 0; i < LD_GENOME_LEN; i += 16) touch ^= (unsigned)__double2loint(__ldca(row + i));
                 if (touch == 0x9e3779b9u) wrow[0].x = 0.0; // keeps the loads alive; rewritten just below
 #pragma unroll
                 for (int i = 0; i < kSmemDoubles / 2; ++i) {
                     double2 w;
-                    w.x = __ldg(row + stored_to_genome(kTmemDoubles + 2 * i));
-                    w.y = __ldg(row + stored_to_genome(kTmemDoubles + 2 * i + 1));
+                    w.x = __ldca(row + stored_to_genome(kTmemDoubles + 2 * i));
+                    w.y = __ldca(row + stored_to_genome(kTmemDoubles + 2 * i + 1));
                     wrow[i] = w;
                 }
                 idx = who;
@@ -440,7 +460,14 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
         if (flying == 0u) {
             const unsigned pending = __ballot_sync(0xffffffffu, slot >= 0);
             if (pending == 0u && !more) break;
-            if (pending != 0u) __nanosleep(500); // wait for a drone to be parked (or for the last one to land)
+            if (pending != 0u) { // wait for rows to arrive, for a drone to be parked, or for the last one to land
+                __nanosleep(500);
+                if (globaltimer_ns() - t_start > kWaitLimitNs) { // never in a healthy run: do not hang the GPU
+                    if (q.error) *q.error = 1;
+                    slot = -1;
+                    more = false;
+                }
+            }
             continue;
         }
 
@@ -496,9 +523,15 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
                 publish<MODE>(p, d, a_last, idx, records, final_state);
                 if (q.cap) atomicAdd(q.done, 1ull);
             } else {
-                // segment boundary: give the lane up only if some drone is waiting for one
-                const unsigned long long produced = (unsigned long long)n + (q.cap ? *(volatile unsigned long long*)q.tail : 0ull);
-                if (q.cap && *(volatile unsigned long long*)q.head < produced) {
+                // segment boundary: give the lane up only if some drone is waiting for one, i.e. if the next
+                // slot to be claimed is filled (a fresh row that has arrived, or a parked drone)
+                bool wanted = false;
+                if (q.cap) {
+                    const long long next = (long long)*(volatile unsigned long long*)q.head;
+                    if (next < n) wanted = q.arrived == nullptr || next < (long long)*(volatile const unsigned long long*)q.arrived;
+                    else wanted = next < n + (long long)*(volatile unsigned long long*)q.tail;
+                }
+                if (wanted) {
                     park_drone(d, q.park + idx * kParkDoubles);
                     __threadfence();
                     const unsigned long long at = atomicAdd(q.tail, 1ull);
@@ -1149,7 +1182,7 @@ int check_params(const ld_params* p) {
 // flies the whole episode (the case segments exist for).  With W = drones / lanes, q segments turn W waves
 // of H steps into ceil(q W) waves of H/q steps; every extra segment costs one re-staging of the brain
 // (~17 steps, measured on B200).  A population whose waves already divide evenly stays unsegmented.
-int auto_slice(long long n, long long lanes, int H) {
+int auto_slice(long long n, long long lanes, int H, bool streamed) {
     constexpr int kMinSlice = 125;
     constexpr double kRestageSteps = 17.0;
     if (n <= lanes || H < 2 * kMinSlice) return H;
@@ -1167,11 +1200,15 @@ int auto_slice(long long n, long long lanes, int H) {
             best_q = q;
         }
     }
+    // rows that arrive while the kernel runs start the lanes at different times: finer segments even that out
+    // (measured on B200: 65,536 survivors end to end 8.22 ms with 2 segments, 8.08 ms with 4)
+    if (streamed && best_q > 1 && (H + 2 * best_q - 1) / (2 * best_q) >= kMinSlice) best_q *= 2;
     return (H + best_q - 1) / best_q;
 }
 
 int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* records, double* final_state,
-               int64_t* work_counter, double* trace, cudaStream_t s, bool f32 = false) {
+               int64_t* work_counter, double* trace, cudaStream_t s, bool f32 = false,
+               const unsigned long long* arrived = nullptr, int* error = nullptr) {
     int rc = ensure_device();
     if (rc) return rc;
     if (n == 0) return LD_OK;
@@ -1200,7 +1237,9 @@ int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* 
     memset(&q, 0, sizeof(q));
     q.head = reinterpret_cast<unsigned long long*>(work_counter);
     q.slice = H > 1 ? H : 1;
-    const int slice = p->slice_steps == 0 ? auto_slice(n, ctas * kCtaThreads, H) : p->slice_steps;
+    q.arrived = arrived;
+    q.error = error;
+    const int slice = p->slice_steps == 0 ? auto_slice(n, ctas * kCtaThreads, H, arrived != nullptr) : p->slice_steps;
     void* scratch = nullptr;
     if (!trace && slice > 0 && slice < H && n > ctas * kCtaThreads && n < 0x7fffffffLL) {
         const long long segments = ((long long)H + slice - 1) / slice;
@@ -1281,6 +1320,114 @@ int ws_reserve(size_t chunk, bool want_state) {
     return LD_OK;
 }
 
+// ---- fp64 host-buffer path: ONE persistent launch, rows streamed in behind it ---------------------
+// The kernel starts on an empty genome matrix; the copy engine delivers it in chunks and raises
+// `arrived` after each one (an 8-byte copy from a pinned table, stream-ordered behind the chunk).  Lanes
+// whose drone is not there yet wait in the queue logic of the kernel.  Compared with chunk-sized
+// launches this keeps every SM in one work queue, so segments and refills balance the whole population.
+constexpr int64_t kHostBatchMax = 4ll << 20; // drones per launch (10.5 GB of genomes)
+constexpr int kHostChunksMax = 4096;
+struct StreamWs {
+    int device = -1;
+    double* genomes = nullptr;
+    ld_record* records = nullptr;
+    double* state = nullptr;
+    unsigned long long* ctl = nullptr;      // [0] arrived, [1] queue head, [2] error flag
+    unsigned long long* h_counts = nullptr; // pinned [kHostChunksMax]
+    int* h_error = nullptr;                 // pinned
+    size_t cap_drones = 0, cap_state = 0;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t armed = nullptr;
+};
+thread_local StreamWs g_sws;
+
+void sws_release() {
+    if (g_sws.genomes) cudaFree(g_sws.genomes);
+    if (g_sws.records) cudaFree(g_sws.records);
+    if (g_sws.state) cudaFree(g_sws.state);
+    if (g_sws.ctl) cudaFree(g_sws.ctl);
+    if (g_sws.h_counts) cudaFreeHost(g_sws.h_counts);
+    if (g_sws.h_error) cudaFreeHost(g_sws.h_error);
+    if (g_sws.compute) cudaStreamDestroy(g_sws.compute);
+    if (g_sws.copy) cudaStreamDestroy(g_sws.copy);
+    if (g_sws.armed) cudaEventDestroy(g_sws.armed);
+    g_sws = StreamWs();
+}
+
+int sws_reserve(size_t drones, bool want_state) {
+    int dev = 0;
+    LD_CUDA(cudaGetDevice(&dev));
+    if (g_sws.device != dev) {
+        sws_release();
+        LD_CUDA(cudaMalloc((void**)&g_sws.ctl, 4 * sizeof(unsigned long long)));
+        LD_CUDA(cudaHostAlloc((void**)&g_sws.h_counts, kHostChunksMax * sizeof(unsigned long long), cudaHostAllocDefault));
+        LD_CUDA(cudaHostAlloc((void**)&g_sws.h_error, sizeof(int), cudaHostAllocDefault));
+        LD_CUDA(cudaStreamCreateWithFlags(&g_sws.compute, cudaStreamNonBlocking));
+        LD_CUDA(cudaStreamCreateWithFlags(&g_sws.copy, cudaStreamNonBlocking));
+        LD_CUDA(cudaEventCreateWithFlags(&g_sws.armed, cudaEventDisableTiming));
+        g_sws.device = dev;
+    }
+    if (g_sws.cap_drones < drones) {
+        if (g_sws.genomes) cudaFree(g_sws.genomes);
+        if (g_sws.records) cudaFree(g_sws.records);
+        if (g_sws.state) cudaFree(g_sws.state);
+        g_sws.genomes = nullptr; g_sws.records = nullptr; g_sws.state = nullptr;
+        g_sws.cap_drones = g_sws.cap_state = 0;
+        LD_CUDA(cudaMalloc((void**)&g_sws.genomes, drones * LD_GENOME_LEN * sizeof(double)));
+        LD_CUDA(cudaMalloc((void**)&g_sws.records, drones * sizeof(ld_record)));
+        g_sws.cap_drones = drones;
+    }
+    if (want_state && g_sws.cap_state < drones) {
+        if (g_sws.state) cudaFree(g_sws.state);
+        g_sws.state = nullptr; g_sws.cap_state = 0;
+        LD_CUDA(cudaMalloc((void**)&g_sws.state, g_sws.cap_drones * LD_STATE_LEN * sizeof(double)));
+        g_sws.cap_state = g_sws.cap_drones;
+    }
+    return LD_OK;
+}
+
+// one launch over rows [0, m) of the host matrix `genomes`
+int fly_streamed_batch(const ld_params* params, const double* genomes, int64_t m, ld_record* records, double* final_state) {
+    StreamWs& w = g_sws;
+    const int64_t wave = (int64_t)g_dev.sms * kCtaThreads;
+    // chunks: eighths of a wave (2368 drones = 5.9 MB, the first lanes start after ~0.1 ms) until the first
+    // wave is in, then half waves (every chunk costs one extra 8-byte copy on the copy engine)
+    const int64_t small = wave / 8 > 1024 ? wave / 8 : 1024;
+    int64_t big = 4 * small;
+    if ((m + big - 1) / big + 8 > kHostChunksMax) big = (m + kHostChunksMax - 9) / (kHostChunksMax - 8);
+    LD_CUDA(cudaMemsetAsync(w.ctl, 0, 4 * sizeof(unsigned long long), w.compute));
+    LD_CUDA(cudaEventRecord(w.armed, w.compute)); // BEFORE the kernel: the copy stream waits for the reset only
+    int rc = launch_fly(params, w.genomes, m, w.records, final_state ? w.state : nullptr, reinterpret_cast<int64_t*>(w.ctl + 1),
+                        nullptr, w.compute, false, w.ctl, reinterpret_cast<int*>(w.ctl + 2));
+    if (rc) return rc;
+    // from here on the kernel is waiting for rows: whatever happens, `arrived` must reach m
+    cudaError_t e = cudaStreamWaitEvent(w.copy, w.armed, 0);
+    int k = 0;
+    for (int64_t off = 0; off < m && e == cudaSuccess; ++k) {
+        const int64_t chunk = off < wave ? small : big;
+        const int64_t c = (m - off < chunk) ? (m - off) : chunk;
+        e = cudaMemcpyAsync(w.genomes + off * LD_GENOME_LEN, genomes + off * LD_GENOME_LEN, (size_t)c * LD_GENOME_LEN * sizeof(double),
+                            cudaMemcpyHostToDevice, w.copy);
+        off += c;
+        w.h_counts[k] = (unsigned long long)off;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(w.ctl, w.h_counts + k, sizeof(unsigned long long), cudaMemcpyHostToDevice, w.copy);
+    }
+    if (e != cudaSuccess) { // release the kernel (its results are discarded) before reporting
+        w.h_counts[kHostChunksMax - 1] = (unsigned long long)m;
+        cudaMemcpy(w.ctl, w.h_counts + kHostChunksMax - 1, sizeof(unsigned long long), cudaMemcpyHostToDevice);
+        cudaStreamSynchronize(w.compute);
+        return fail(LD_ERR_CUDA, "streaming genomes to the device", e);
+    }
+    LD_CUDA(cudaMemcpyAsync(records, w.records, (size_t)m * sizeof(ld_record), cudaMemcpyDeviceToHost, w.compute));
+    if (final_state)
+        LD_CUDA(cudaMemcpyAsync(final_state, w.state, (size_t)m * LD_STATE_LEN * sizeof(double), cudaMemcpyDeviceToHost, w.compute));
+    LD_CUDA(cudaMemcpyAsync(w.h_error, w.ctl + 2, sizeof(int), cudaMemcpyDeviceToHost, w.compute));
+    LD_CUDA(cudaStreamSynchronize(w.copy));
+    LD_CUDA(cudaStreamSynchronize(w.compute));
+    if (*w.h_error) return fail(LD_ERR_CUDA, "episode kernel gave up waiting for its work queue");
+    return LD_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -1346,7 +1493,15 @@ static int fly_mlp_host_impl(const ld_params* params, const double* genomes, int
     if (!genomes || !records) return fail(LD_ERR_INVALID_ARG, "NULL host buffer");
     rc = ensure_device();
     if (rc) return rc;
-    // Pipeline over kHostStreams streams / buffers.  A chunk is a quarter of a wave (37 of 148 SMs):
+    if (!f32) {
+        const int64_t batch = n < kHostBatchMax ? n : kHostBatchMax;
+        rc = sws_reserve((size_t)batch, final_state != nullptr);
+        for (int64_t off = 0; off < n && rc == LD_OK; off += batch)
+            rc = fly_streamed_batch(params, genomes + off * LD_GENOME_LEN, (n - off < batch) ? (n - off) : batch, records + off,
+                                    final_state ? final_state + off * LD_STATE_LEN : nullptr);
+        return rc;
+    }
+    // fp32 mode: pipeline over kHostStreams streams / buffers.  A chunk is a quarter of a wave (37 of 148 SMs):
     // kernels of different chunks are resident on disjoint SMs at the same time (a CTA owns its SM's
     // Tensor Memory), so the machine fills up after four small H2D copies instead of one big one
     // and every later copy / record read-back hides behind the kernels.  Big populations use
@@ -1536,6 +1691,7 @@ int ld_drone_step_host(const ld_params* params, int what, const double* genomes,
 
 void ld_release_workspace(void) {
     ws_release();
+    sws_release();
     int dev = 0;
     cudaMemPool_t pool;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);

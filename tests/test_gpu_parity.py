@@ -115,6 +115,12 @@ def test_episode_segments_do_not_change_results(pop, gen, slice_steps):
         assert st0.cpu().numpy().tobytes() == st1.cpu().numpy().tobytes()
     rec2, _ = pop.fly_population_device(gt, p)  # the kernel variant without the state output
     assert torch.equal(rec0, rec2)
+    # host buffers: one launch that starts before its rows have arrived (pageable and pinned source)
+    rec_h, st_h = pop.fly_population_host(genomes, p, want_state=True)
+    assert rec_h.tobytes() == r0.tobytes() and st_h.tobytes() == st0.cpu().numpy().tobytes()
+    pinned = torch.from_numpy(genomes).pin_memory()
+    rec_p, _ = pop.fly_population_host(pinned.numpy(), p)
+    assert rec_p.tobytes() == r0.tobytes()
 
 
 @pytest.mark.parametrize("n", [0, 1, 31, 33, 95, 97, 14207, 14209])
