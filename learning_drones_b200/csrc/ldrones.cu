@@ -1395,29 +1395,25 @@ int fly_streamed_batch(const ld_params* params, const double* genomes, int64_t m
     const int64_t small = wave / 8 > 1024 ? wave / 8 : 1024;
     int64_t big = 4 * small;
     if ((m + big - 1) / big + 8 > kHostChunksMax) big = (m + kHostChunksMax - 9) / (kHostChunksMax - 8);
-    LD_CUDA(cudaMemsetAsync(w.ctl, 0, 4 * sizeof(unsigned long long), w.compute));
-    LD_CUDA(cudaEventRecord(w.armed, w.compute)); // BEFORE the kernel: the copy stream waits for the reset only
+    // Every copy is queued BEFORE the kernel is launched: the copy engine works through them on its own, so
+    // the kernel can never be left waiting for a copy the host has not issued yet (tools that make launches
+    // synchronous — profilers, CUDA_LAUNCH_BLOCKING — would otherwise stall it until kWaitLimitNs).
+    LD_CUDA(cudaMemsetAsync(w.ctl, 0, 4 * sizeof(unsigned long long), w.copy));
+    LD_CUDA(cudaEventRecord(w.armed, w.copy));
+    LD_CUDA(cudaStreamWaitEvent(w.compute, w.armed, 0)); // the kernel only waits for the counters to be reset
+    int k = 0;
+    for (int64_t off = 0; off < m; ++k) {
+        const int64_t chunk = off < wave ? small : big;
+        const int64_t c = (m - off < chunk) ? (m - off) : chunk;
+        LD_CUDA(cudaMemcpyAsync(w.genomes + off * LD_GENOME_LEN, genomes + off * LD_GENOME_LEN, (size_t)c * LD_GENOME_LEN * sizeof(double),
+                                cudaMemcpyHostToDevice, w.copy));
+        off += c;
+        w.h_counts[k] = (unsigned long long)off;
+        LD_CUDA(cudaMemcpyAsync(w.ctl, w.h_counts + k, sizeof(unsigned long long), cudaMemcpyHostToDevice, w.copy));
+    }
     int rc = launch_fly(params, w.genomes, m, w.records, final_state ? w.state : nullptr, reinterpret_cast<int64_t*>(w.ctl + 1),
                         nullptr, w.compute, false, w.ctl, reinterpret_cast<int*>(w.ctl + 2));
     if (rc) return rc;
-    // from here on the kernel is waiting for rows: whatever happens, `arrived` must reach m
-    cudaError_t e = cudaStreamWaitEvent(w.copy, w.armed, 0);
-    int k = 0;
-    for (int64_t off = 0; off < m && e == cudaSuccess; ++k) {
-        const int64_t chunk = off < wave ? small : big;
-        const int64_t c = (m - off < chunk) ? (m - off) : chunk;
-        e = cudaMemcpyAsync(w.genomes + off * LD_GENOME_LEN, genomes + off * LD_GENOME_LEN, (size_t)c * LD_GENOME_LEN * sizeof(double),
-                            cudaMemcpyHostToDevice, w.copy);
-        off += c;
-        w.h_counts[k] = (unsigned long long)off;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(w.ctl, w.h_counts + k, sizeof(unsigned long long), cudaMemcpyHostToDevice, w.copy);
-    }
-    if (e != cudaSuccess) { // release the kernel (its results are discarded) before reporting
-        w.h_counts[kHostChunksMax - 1] = (unsigned long long)m;
-        cudaMemcpy(w.ctl, w.h_counts + kHostChunksMax - 1, sizeof(unsigned long long), cudaMemcpyHostToDevice);
-        cudaStreamSynchronize(w.compute);
-        return fail(LD_ERR_CUDA, "streaming genomes to the device", e);
-    }
     LD_CUDA(cudaMemcpyAsync(records, w.records, (size_t)m * sizeof(ld_record), cudaMemcpyDeviceToHost, w.compute));
     if (final_state)
         LD_CUDA(cudaMemcpyAsync(final_state, w.state, (size_t)m * LD_STATE_LEN * sizeof(double), cudaMemcpyDeviceToHost, w.compute));
