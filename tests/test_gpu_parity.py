@@ -123,6 +123,28 @@ def test_episode_segments_do_not_change_results(pop, gen, slice_steps):
     assert rec_p.tobytes() == r0.tobytes()
 
 
+@pytest.mark.parametrize("extra,slice_steps,batch", [(1, 7, 1), (33, 13, 32), (5000, 1, 0)])
+def test_episode_segments_stress(pop, gen, extra, slice_steps, batch):
+    """Tiny segments (down to one step), a population just above one wave, extreme refill batches."""
+    import torch
+
+    from learning_drones_b200 import _lib
+
+    wave = int(_lib.load().ld_wave_size())
+    rng = np.random.default_rng(extra)
+    n = wave + extra
+    genomes = np.concatenate([gen.random_brains(n - n // 3, rng), gen.survivors(n // 3, rng)])[rng.permutation(n)]
+    gt = torch.from_numpy(genomes).cuda()
+    p = make_params(60)
+    p.slice_steps = -1
+    rec0, st0 = pop.fly_population_device(gt, p, want_state=True)
+    p.slice_steps, p.refill_batch = slice_steps, batch
+    rec1, st1 = pop.fly_population_device(gt, p, want_state=True)
+    assert torch.equal(rec0, rec1) and st0.cpu().numpy().tobytes() == st1.cpu().numpy().tobytes()
+    rec_h, _ = pop.fly_population_host(genomes, p)
+    assert rec_h.tobytes() == pop.records_to_numpy(rec0).tobytes()
+
+
 @pytest.mark.parametrize("n", [0, 1, 31, 33, 95, 97, 14207, 14209])
 def test_ragged_population_sizes(pop, oracle, gen, n):
     rng = np.random.default_rng(100 + n)
