@@ -65,22 +65,27 @@ __device__ __forceinline__ void trig_fast(Drone& d) {
 }
 
 // |angle| beyond the fast reduction's range (never seen in practice: angles are unwrapped but
-// episodes end long before): redo everything with CUDA's libm (Payne-Hanek reduction).  One
-// warp-uniform, normally-not-taken branch; kept apart from trig_fast so that the straight-line
-// part can share a basic block with the MLP.  Must run before the next physics_step.
-// `live`: lanes without a drone keep stepping a stale (possibly diverged) state; they must not drag
-// the warp into this branch.
-__device__ __forceinline__ void trig_fallback(Drone& d, bool live = true) {
+// episodes end long before): redo everything with CUDA's libm (Payne-Hanek reduction).  Kept apart
+// from trig_fast so that the straight-line part can share a basic block with the MLP: the episode
+// kernel folds `trig_is_big` into the vote that ends its hot loop and calls `trig_slow` per lane
+// outside of it.  Must run before the next physics_step.
+__device__ __forceinline__ bool trig_is_big(const Drone& d) {
+    return !(fabs(d.x[3]) <= kTrigFastMax && fabs(d.x[4]) <= kTrigFastMax && fabs(d.x[5]) <= kTrigFastMax);
+}
+
+__device__ __forceinline__ void trig_slow(Drone& d) {
     Trig& g = d.trig;
-    const double roll = d.x[3], pitch = d.x[4], yaw = d.x[5];
-    const bool big = live && !(fabs(roll) <= kTrigFastMax && fabs(pitch) <= kTrigFastMax && fabs(yaw) <= kTrigFastMax);
+    sincos(d.x[3], &g.sr, &g.cr);
+    sincos(d.x[4], &g.sp, &g.cp);
+    sincos(d.x[5], &g.sy, &g.cy);
+    trig_finish(g, tan(d.x[4]), recip(g.cp));
+}
+
+// warp-converged form: one warp-uniform, normally-not-taken branch
+__device__ __forceinline__ void trig_fallback(Drone& d) {
+    const bool big = trig_is_big(d);
     if (__any_sync(0xffffffffu, big)) {
-        if (big) {
-            sincos(roll, &g.sr, &g.cr);
-            sincos(pitch, &g.sp, &g.cp);
-            sincos(yaw, &g.sy, &g.cy);
-            trig_finish(g, tan(pitch), recip(g.cp));
-        }
+        if (big) trig_slow(d);
     }
 }
 

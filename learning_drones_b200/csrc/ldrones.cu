@@ -490,7 +490,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             t_end = kPollSteps;
         }
         double a_last[6];
-        bool crashed, done;
+        bool crashed, done, big;
         do {
             int u;
             uint32_t w0[32];
@@ -504,10 +504,9 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
                 if (live) write_state(d, a_last, trace + (size_t)t * LD_STATE_LEN);
             }
             // next step's trigonometry and this step's brain: independent, one basic block, interleaved
-            // by the scheduler; the (never taken) large-angle fallback branch comes after both
+            // by the scheduler
             trig_fast(d);
             brain(d, taddr, wrow, neg_beta, MODE != kPlain && crashed, w0);
-            trig_fallback(d);
             if (MODE == kTrace) {
                 if (live && !crashed) {
 #pragma unroll
@@ -516,7 +515,9 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             }
             t += counting ? 1 : 0;
             done = counting && (crashed || t >= t_end);
-        } while (!__any_sync(0xffffffffu, done));
+            big = trig_is_big(d); // the (never seen) large-angle case leaves the hot loop through the same vote
+        } while (!__any_sync(0xffffffffu, done || big));
+        if (big) trig_slow(d);
         if (done && live) {
             bool leave = true;
             if (crashed || t >= H) {
