@@ -268,14 +268,15 @@ __device__ __forceinline__ void mlp_smem_tail(Mlp& m, const double2* __restrict_
     }
 }
 
-// chunks C..15 with the next chunk's tcgen05.ld in flight while chunk C is consumed
+// chunks C..15 with the next TWO chunks' tcgen05.ld in flight while chunk C is consumed (`cur` holds chunk C,
+// `nxt` was requested one chunk ago, `nx2` is free)
 template <int C>
-__device__ __forceinline__ void mlp_tmem_chunks(Mlp& m, uint32_t taddr, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
-    if constexpr (C + 1 < kChunks) tmem_ld32(nxt, taddr + 32 * (C + 1));
+__device__ __forceinline__ void mlp_tmem_chunks(Mlp& m, uint32_t taddr, uint32_t (&cur)[32], uint32_t (&nxt)[32], uint32_t (&nx2)[32]) {
+    if constexpr (C + 2 < kChunks) tmem_ld32(nx2, taddr + 32 * (C + 2));
     mlp_chunk<C>(m, cur);
     if constexpr (C + 1 < kChunks) {
         tmem_wait_ld(nxt);
-        mlp_tmem_chunks<C + 1>(m, taddr, nxt, cur);
+        mlp_tmem_chunks<C + 1>(m, taddr, nxt, nx2, cur);
     }
 }
 
@@ -292,9 +293,10 @@ __device__ __forceinline__ void brain(Drone& d, uint32_t taddr, const double2* _
         m.in[12 + i] = d.coin[i];
     }
     // chunk 0 was requested before the physics of this step (its latency hides behind it)
-    uint32_t b[32];
+    uint32_t b[32], c[32];
+    tmem_ld32(b, taddr + 32);
     tmem_wait_ld(a);
-    mlp_tmem_chunks<0>(m, taddr, a, b);
+    mlp_tmem_chunks<0>(m, taddr, a, b, c);
     mlp_smem_tail(m, wrow);
 #pragma unroll
     for (int j = 0; j < kOut; ++j) {
