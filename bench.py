@@ -333,7 +333,8 @@ def main():
                 "population": D * world, "timesteps": H,
                 "active_drone_steps_per_generation": [h["active_steps"] for h in hist],
                 "best_score": [h["global_best_score"] for h in hist],
-                "note": "generation 0 = the bench population, later generations = its GA offspring (most crash early)"}
+                "note": "one untimed warm-up generation flies the bench population; the timed generations are its GA offspring "
+                        "(most crash early), enqueued back to back with one host synchronisation at the end"}
         del ev
 
     if rank == 0:

@@ -265,6 +265,17 @@ int ld_ga_step_p2p_device(const ld_ga_params* ga, const ld_peer_table* peers, co
  * [3]=sum coins, [4]=crashed count.  Device pointers. */
 int ld_reduce_records_device(const ld_record* records, int64_t n, int64_t* stats5, void* stream);
 
+/* ---- best-of-run tracking on the device: evolve/evolution.py:77-83 ----------
+ * Reads stats5 of the generation just flown (ld_reduce_records_device).  If there is no global best yet
+ * (best2[1] == 0) or stats5[1] > best2[0]: best2 = {stats5[1], 1} and best_genome[LD_GENOME_LEN] = row
+ * stats5[2] of the population — `population` [n][LD_GENOME_LEN], or, when it is NULL, the sharded
+ * population behind `peers` (row r lives on rank r / shard_rows; read over NVLink peer memory).
+ * history7 (may be NULL) receives {generation, best reward, best index, global best reward, active
+ * drone-steps, coins, crashed} so that a host loop can run many generations without synchronising.
+ * Device pointers, stream-ordered. */
+int ld_track_best_device(const int64_t* stats5, const double* population, const ld_peer_table* peers, int64_t generation,
+                         int64_t* best2, double* best_genome, int64_t* history7, void* stream);
+
 /* Roofline denominator: measured fp64 (non-tensor) FMA throughput of the current device in
  * TFLOP/s (FMA = 2 flop), from a register-only DFMA-chain microbenchmark; optionally the same
  * as DFMA per max-clock cycle per SM. */

@@ -30,6 +30,7 @@ EXPORTS = (
     "ld_fly_mlp_f32_device",
     "ld_fly_mlp_f32_host",
     "ld_drone_step_host",
+    "ld_track_best_device",
 )
 
 
@@ -74,6 +75,8 @@ def load():
     L.ld_fly_mlp_f64_trace_device.restype = C.c_int
     L.ld_reduce_records_device.argtypes = [vp, i64, vp, vp]
     L.ld_reduce_records_device.restype = C.c_int
+    L.ld_track_best_device.argtypes = [vp, vp, C.POINTER(LdPeerTable), i64, vp, vp, vp, vp]
+    L.ld_track_best_device.restype = C.c_int
     L.ld_release_workspace.restype = None
     L.ld_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ld_measure_fp64_peak.restype = C.c_int

@@ -1100,6 +1100,36 @@ __global__ void __launch_bounds__(256) reduce_records_kernel(const ld_record* __
     }
 }
 
+// evolve/evolution.py:77-83 on the device (one block): keep the best drone seen so far
+__global__ void __launch_bounds__(320) track_best_kernel(const long long* __restrict__ stats, const double* __restrict__ population,
+                                                         const __grid_constant__ ld_peer_table peers, long long generation,
+                                                         long long* __restrict__ best2, double* __restrict__ best_genome,
+                                                         long long* __restrict__ history7) {
+    const long long score = stats[1], index = stats[2];
+    const bool improved = best2[1] == 0 || score > best2[0];
+    if (improved && threadIdx.x < LD_GENOME_LEN) {
+        const double* row = population ? population + index * LD_GENOME_LEN
+                                       : peers.shard[index / peers.shard_rows] + (index % peers.shard_rows) * LD_GENOME_LEN;
+        best_genome[threadIdx.x] = row[threadIdx.x];
+    }
+    __syncthreads(); // every thread has read best2 before it changes
+    if (threadIdx.x == 0) {
+        if (improved) {
+            best2[0] = score;
+            best2[1] = 1;
+        }
+        if (history7) {
+            history7[0] = generation;
+            history7[1] = score;
+            history7[2] = index;
+            history7[3] = improved ? score : best2[0];
+            history7[4] = stats[0];
+            history7[5] = stats[3];
+            history7[6] = stats[4];
+        }
+    }
+}
+
 __global__ void finalize_stats_kernel(unsigned long long* stats, long long n) {
     const unsigned long long k = stats[1];
     if (n > 0) {
@@ -1563,6 +1593,26 @@ int ld_reduce_records_device(const ld_record* records, int64_t n, int64_t* stats
         reduce_records_kernel<<<(unsigned)blocks, 256, 0, s>>>(records, n, st);
     }
     finalize_stats_kernel<<<1, 1, 0, s>>>(st, n);
+    LD_CUDA(cudaGetLastError());
+    return LD_OK;
+}
+
+int ld_track_best_device(const int64_t* stats5, const double* population, const ld_peer_table* peers, int64_t generation,
+                         int64_t* best2, double* best_genome, int64_t* history7, void* stream) {
+    if (!stats5 || !best2 || !best_genome || (!population && !peers)) return fail(LD_ERR_INVALID_ARG, "NULL argument");
+    ld_peer_table table;
+    memset(&table, 0, sizeof(table));
+    if (!population) {
+        if (peers->world < 1 || peers->world > LD_MAX_PEERS || peers->shard_rows < 1) return fail(LD_ERR_INVALID_ARG, "bad peer table");
+        for (int r = 0; r < peers->world; ++r)
+            if (!peers->shard[r]) return fail(LD_ERR_INVALID_ARG, "peer table: NULL shard pointer");
+        table = *peers;
+    }
+    int rc = ensure_device();
+    if (rc) return rc;
+    track_best_kernel<<<1, 320, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(stats5), population, table, generation,
+                                                          reinterpret_cast<long long*>(best2), best_genome,
+                                                          reinterpret_cast<long long*>(history7));
     LD_CUDA(cudaGetLastError());
     return LD_OK;
 }

@@ -20,7 +20,7 @@ import numpy as np
 from .. import _lib
 from .._abi import GENOME_LEN, make_ga_params, make_params, make_peer_table
 from ..distributed import allgather_records, shard_bounds
-from ..population import fly_population_device, reduce_records
+from ..population import fly_population_device, reduce_records_device
 
 
 class GpuEvolution:
@@ -45,8 +45,12 @@ class GpuEvolution:
         self.params = make_params(timesteps=timesteps, **fly_kw)
         self.seed, self.generation = int(seed), 0
         self.hyper = dict(p_tournament=p_tournament, p_crossover=p_crossover, mutation_rate=mutation_rate, mutation_sigma=mutation_sigma)
-        self.global_best_score = None
+        # best-of-run tracking lives on the device (ld_track_best_device): {score, valid}, the genome, and one
+        # row of statistics per generation, so that run() never has to wait for the GPU between generations
+        self._best = torch.zeros(2, dtype=torch.int64, device=self.device)
         self.global_best_genome = torch.empty(GENOME_LEN, dtype=torch.float64, device=self.device)
+        self._stats = torch.empty(5, dtype=torch.int64, device=self.device)
+        self._history = torch.zeros((0, 7), dtype=torch.int64, device=self.device)
         self.records = None  # fitness records of the generation flown last (whole population)
         self.p2p = False
         if self.world > 1 and p2p is not False:
@@ -79,34 +83,30 @@ class GpuEvolution:
         torch.cuda.synchronize(self.device)
         self.dist.barrier()
 
-    def _row(self, index):
-        """Genome row `index` of the CURRENT population (a peer-memory view in p2p mode)."""
-        if not self.p2p:
-            return self.population[index]
-        owner, local = divmod(int(index), self.shard_rows)
-        if owner == self.rank:
-            return self._bufs[self._cur][local]
-        peer = self._handles[self._cur].get_buffer(owner, (self.shard_rows, GENOME_LEN), self.torch.float64)
-        return peer[local]
-
     @property
     def local_population(self):
         return self._bufs[self._cur] if self.p2p else self.population[self.lo:self.hi]
 
-    # -- one generation: evolve/evolution.py:50-107 ------------------------------------------------
-    def step(self):
+    @property
+    def global_best_score(self):
+        """Best reward seen so far (evolution.py:80-83); None before the first generation.  Synchronises."""
+        score, valid = self._best.cpu().tolist()
+        return score if valid else None
+
+    # -- one generation: evolve/evolution.py:50-107, enqueued on the current stream without waiting ---
+    def _enqueue_generation(self, history_row):
         torch = self.torch
         L = _lib.load()
         local_records, _ = fly_population_device(self.local_population, self.params)
         self.records = allgather_records(local_records, n_global=self.n) if self.dist else local_records
-        stats = reduce_records(self.records)  # np.argmax(scores), evolution.py:77-78
-        best_score, best_index = stats["best_reward"], stats["best_index"]
-        if self.global_best_score is None or best_score > self.global_best_score:  # :80-83
-            self.global_best_score = best_score
-            self.global_best_genome.copy_(self._row(best_index))
+        reduce_records_device(self.records, self._stats)  # np.argmax(scores), evolution.py:77-78
         ga = make_ga_params(self.seed, self.generation, **self.hyper)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
+            # global best, :80-83 — the row is read from the current population (peer memory in p2p mode)
+            _lib.check(L.ld_track_best_device(self._stats.data_ptr(), None if self.p2p else self.population.data_ptr(),
+                                              C.byref(self._tables[self._cur]) if self.p2p else None, self.generation,
+                                              self._best.data_ptr(), self.global_best_genome.data_ptr(), history_row.data_ptr(), stream))
             if self.p2p:
                 children = self._bufs[1 - self._cur]
                 _lib.check(L.ld_ga_step_p2p_device(C.byref(ga), C.byref(self._tables[self._cur]), self.records.data_ptr(), self.n,
@@ -125,12 +125,25 @@ class GpuEvolution:
                 self.next_population[0].copy_(self.global_best_genome)  # elitism, :105-107
                 self.population, self.next_population = self.next_population, self.population
         self.generation += 1
-        return dict(generation=self.generation - 1, best_score=best_score, best_index=best_index,
-                    global_best_score=self.global_best_score, active_steps=stats["active_steps"], coins=stats["coins"],
-                    crashed=stats["crashed"])
+
+    @staticmethod
+    def _history_dict(row):
+        g, best, index, glob, steps, coins, crashed = row
+        return dict(generation=g, best_score=best, best_index=index, global_best_score=glob, active_steps=steps, coins=coins,
+                    crashed=crashed)
 
     def run(self, n_generations: int):
-        return [self.step() for _ in range(n_generations)]
+        """`n_generations` of the loop, enqueued back to back; one synchronisation at the end to read the
+        per-generation statistics (a list of dicts like step()'s)."""
+        torch = self.torch
+        history = torch.zeros((n_generations, 7), dtype=torch.int64, device=self.device)
+        for g in range(n_generations):
+            self._enqueue_generation(history[g])
+        self._history = torch.cat([self._history, history])
+        return [self._history_dict(r) for r in history.cpu().tolist()]
+
+    def step(self):
+        return self.run(1)[0]
 
     def best_genome(self) -> np.ndarray:
         return self.global_best_genome.cpu().numpy()

@@ -112,17 +112,24 @@ def record_coins(records):
     return records.view(torch.int32)[:, 2]
 
 
-def reduce_records(records):
-    """Warp-shuffle reduction on the device -> dict(active_steps, best_reward, best_index, coins, crashed)."""
+def reduce_records_device(records, stats=None):
+    """Warp-shuffle reduction on the device -> int64[5] CUDA tensor (active_steps, best_reward, best_index,
+    coins, crashed); asynchronous on the current stream."""
     import torch
 
     L = _lib.load()
     n = records.shape[0]
     with torch.cuda.device(records.device):
-        stats = torch.empty(5, dtype=torch.int64, device=records.device)
+        if stats is None:
+            stats = torch.empty(5, dtype=torch.int64, device=records.device)
         stream = torch.cuda.current_stream(records.device).cuda_stream
         _lib.check(L.ld_reduce_records_device(records.data_ptr(), n, stats.data_ptr(), stream))
-    s = stats.cpu().tolist()
+    return stats
+
+
+def reduce_records(records):
+    """Warp-shuffle reduction on the device -> dict(active_steps, best_reward, best_index, coins, crashed)."""
+    s = reduce_records_device(records).cpu().tolist()
     return dict(active_steps=s[0], best_reward=s[1], best_index=s[2], coins=s[3], crashed=s[4])
 
 

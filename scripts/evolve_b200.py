@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--p-tournament", type=float, default=0.6)
     ap.add_argument("--p-crossover", type=float, default=0.05)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--report-every", type=int, default=10, help="generations enqueued between two host synchronisations")
     ap.add_argument("--out", default=None, help="write the winning genome (314 float64) to this .npy")
     args = ap.parse_args()
 
@@ -42,11 +43,14 @@ def main():
     ev = GpuEvolution(genomes, seed=args.seed, timesteps=args.timesteps, mutation_rate=args.mutation_rate,
                       p_tournament=args.p_tournament, p_crossover=args.p_crossover)
     t0 = time.time()
-    for _ in range(args.generations):
-        h = ev.step()
-        if rank == 0:
-            print(f"Generation {h['generation']}: Best Score: {h['best_score']}, Global Best: {h['global_best_score']}  "
-                  f"(coins {h['coins']}, crashed {h['crashed']}/{args.drones}, {h['active_steps']} drone-steps)")
+    done = 0
+    while done < args.generations:  # generations are enqueued in blocks; the host only waits to print a block
+        block = min(args.report_every, args.generations - done)
+        for h in ev.run(block):
+            if rank == 0:
+                print(f"Generation {h['generation']}: Best Score: {h['best_score']}, Global Best: {h['global_best_score']}  "
+                      f"(coins {h['coins']}, crashed {h['crashed']}/{args.drones}, {h['active_steps']} drone-steps)")
+        done += block
     torch.cuda.synchronize()
     if rank == 0:
         dt = time.time() - t0

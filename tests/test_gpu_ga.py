@@ -103,3 +103,21 @@ def test_gpu_evolution_loop():
     assert ev2.run(5) == hist  # counter-based RNG: reproducible
     assert not np.array_equal(ev.population.cpu().numpy(), genomes)
     assert np.array_equal(ev.population[0].cpu().numpy(), ev.best_genome())
+    assert ev.global_best_score == hist[-1]["global_best_score"]
+    # generation by generation (one host synchronisation each) == enqueued in one block
+    ev3 = GpuEvolution(genomes, seed=1, timesteps=600)
+    assert [ev3.step() for _ in range(5)] == hist
+    assert np.array_equal(ev3.population.cpu().numpy(), ev.population.cpu().numpy())
+    # device-side best tracking == host-side: the best genome is the row that produced the best reward
+    from learning_drones_b200.population import fly_population_device, records_to_numpy
+
+    ev4 = GpuEvolution(genomes, seed=1, timesteps=600)
+    best, best_row = None, None
+    for _ in range(3):
+        pop_before = ev4.population.clone()
+        h = ev4.step()
+        r = records_to_numpy(fly_population_device(pop_before, ev4.params)[0])["reward"]
+        assert h["best_score"] == int(r.max()) and h["best_index"] == int(np.argmax(r))
+        if best is None or h["best_score"] > best:
+            best, best_row = h["best_score"], pop_before[h["best_index"]].cpu().numpy()
+        assert h["global_best_score"] == best and np.array_equal(ev4.best_genome(), best_row)
