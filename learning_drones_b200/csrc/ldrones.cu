@@ -517,9 +517,12 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             }
             t += counting ? 1 : 0;
             done = counting && (crashed || t >= t_end);
-            big = trig_is_big(d); // the (never seen) large-angle case leaves the hot loop through the same vote
-        } while (!__any_sync(0xffffffffu, done || big));
-        if (big) trig_slow(d);
+            // one vote per step: the large-angle case (a few tumbling drones in ten thousand) shares it
+            big = trig_is_big(d);
+            if (!__any_sync(0xffffffffu, done || big)) continue;
+            if (big) trig_slow(d);
+            if (__any_sync(0xffffffffu, done)) break;
+        } while (true);
         if (done && live) {
             bool leave = true;
             if (crashed || t >= H) {
