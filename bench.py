@@ -31,15 +31,15 @@ sys.path.insert(0, ROOT)
 METRIC = "drone-steps/sec (dynamics+brain+reward)"
 UNIT = "drone-steps/s"
 FLOP_PER_STEP = 850.0  # SURVEY.md §8d algorithmic work per drone-step (FMA = 2)
-FP64_INSTR_PER_STEP = 638.0  # executed fp64-pipe instructions per drone-step (ncu source counters, profiles/r01_f_*)
+FP64_INSTR_PER_STEP = 638.0  # executed fp64-pipe instructions per drone-step (ncu source counters, profiles/r01_g_*)
 GENOME_BYTES = 314 * 8
 RECORD_BYTES = 32
 # dram__bytes_read.sum + dram__bytes_write.sum of fly_mlp_f64_kernel for the default workload
-# (65,536 survivors x 2,000 steps), one `ncu --set full` capture: profiles/r01_f_fly_mlp_f64_ncu_full_summary.csv.
-# 2.17x the algorithmic bytes ON PURPOSE: the episode is flown in two segments (ld_params.slice_steps), every
+# (65,536 survivors x 2,000 steps), one `ncu --set full` capture: profiles/r01_g_fly_mlp_f64_ncu_full_summary.csv.
+# 2.18x the algorithmic bytes ON PURPOSE: the episode is flown in two segments (ld_params.slice_steps), every
 # drone is parked once (256 B out + in) and its 2,512-B brain row is read a second time — 0.2 GB of extra
 # traffic (0.8 % of HBM peak for 7 ms) that removes the 13.5 % wave-quantisation loss of 3.46 waves.
-NCU_TRAFFIC_DEFAULT_WORKLOAD = 340272896 + 22029056
+NCU_TRAFFIC_DEFAULT_WORKLOAD = 342274816 + 21697280
 
 
 def population(kind, n, seed=2026):
@@ -365,7 +365,7 @@ def main():
                          "pipe_utilisation": steps_per_launch * FP64_INSTR_PER_STEP / (kernel_ms * 1e-3) / (tf.value * 1e12 / 2.0),
                          "note": "achieved = active drone-steps per launch x 850 algorithmic flop / kernel time; "
                                  "pipe_utilisation = executed fp64-pipe thread-instructions (ncu: 418 DFMA + 116 DMUL + 83 DADD "
-                                 "+ 21 DSETP per drone-step, profiles/r01_f_*) / measured DFMA issue peak; the co-limiter is "
+                                 "+ 21 DSETP per drone-step, profiles/r01_g_*) / measured DFMA issue peak; the co-limiter is "
                                  "dependency latency with one warp per SM sub-partition (brain capacity), DESIGN.md 4"},
             "hbm_roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved_gbs / peaks["hbm_gbs"], "algorithmic_bytes": alg_bytes,
