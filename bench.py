@@ -371,7 +371,9 @@ def main():
                              "frac": achieved_gbs / peaks["hbm_gbs"], "algorithmic_bytes": alg_bytes,
                              "traffic": NCU_TRAFFIC_DEFAULT_WORKLOAD if (D, H, args.population) == (65536, 2000, "survivors") else None,
                              "peak_source": peaks_src,
-                             "note": "compute-bound by construction: 2,544 algorithmic bytes per 2,000-step episode"},
+                             "note": "compute-bound by construction: 2,544 algorithmic bytes per 2,000-step episode; the measured traffic is "
+                                     "2.18x that on purpose (episode flown in two segments: brain row read twice, drone parked once) "
+                                     "— 0.2 GB of idle HBM bandwidth traded for the 13.5 % wave-quantisation loss, DESIGN.md 4"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": D * GENOME_BYTES * world,
                     "d2h_bytes_per_step": D * RECORD_BYTES * world, "api": "ld_fly_mlp_f64_host via fly_population_host (one persistent launch; genome rows stream in behind it)"},
             "gpu_launches": args.steps * world,
