@@ -253,3 +253,29 @@ def test_properties_with_hypothesis():
     threshold()
     shards()
     wiring()
+
+
+def test_best_drone_checkpoint_round_trip(tmp_path):
+    """persist the best drone (evolution.py:85-87) and load it back (fly_best_drone.py:11-14)."""
+    from learning_drones_b200 import checkpoint
+    from learning_drones_b200.drone.drone import Drone
+
+    np.random.seed(5)
+    d = Drone()
+    d.reward, d.coins, d.flight_time, d.crashed, d.distance_to_coin = -4077, 3, 170, True, 1.0 / 3.0
+    path = checkpoint.save_drone(d, tmp_path / "best_drone.json")
+    e = checkpoint.load_drone(path)
+    assert all(np.array_equal(a, b) for a, b in zip(d.controller.weights, e.controller.weights))  # bit for bit
+    assert np.array_equal(d.controller.genome(), e.controller.genome())
+    assert (e.reward, e.coins, e.flight_time, e.crashed, e.distance_to_coin) == (-4077, 3, 170, True, 1.0 / 3.0)
+    assert e.controller.layer_spec == d.controller.layer_spec
+    with pytest.raises(ValueError):
+        checkpoint.save_drone(d, tmp_path / "x.json", fmt="pickle")
+    try:
+        import jsonpickle  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):  # the reference's format is never emulated without its library
+            checkpoint.save_drone(d, tmp_path / "ref.json", fmt="jsonpickle")
+    else:
+        f = checkpoint.load_drone(checkpoint.save_drone(d, tmp_path / "ref.json", fmt="jsonpickle"))
+        assert all(np.array_equal(a, b) for a, b in zip(d.controller.weights, f.controller.weights))
