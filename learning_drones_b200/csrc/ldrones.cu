@@ -1209,6 +1209,7 @@ bool has_extras(const ld_params* p) {
 int check_params(const ld_params* p) {
     if (!p) return fail(LD_ERR_INVALID_ARG, "params is NULL");
     if (p->timesteps < 0) return fail(LD_ERR_INVALID_ARG, "params.timesteps < 0");
+    if (p->timesteps > (1 << 27)) return fail(LD_ERR_INVALID_ARG, "params.timesteps > 2^27 (the running reward is kept in 32 bits)");
     if (!(p->dt > 0.0)) return fail(LD_ERR_INVALID_ARG, "params.dt must be > 0");
     if (!(p->m_total32 > 0.0f)) return fail(LD_ERR_INVALID_ARG, "params.m_total32 must be > 0");
     return LD_OK;

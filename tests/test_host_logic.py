@@ -208,7 +208,10 @@ def test_abi_argument_validation_without_gpu():
     bad = make_params(10)
     bad.dt = 0.0
     assert L.ld_fly_mlp_f64_host(C.byref(bad), None, 1, None, None) == -1
+    long = make_params((1 << 27) + 1)
+    assert L.ld_fly_mlp_f64_host(C.byref(long), None, 1, None, None) == -1 and b"2^27" in L.ld_last_error()
     assert L.ld_fly_mlp_f64_host(C.byref(p), None, 0, None, None) == 0  # empty population is a no-op
+    assert L.ld_track_best_device(None, None, None, 0, None, None, None, None) == -1
     q = make_pid_params()
     q.n_coins = 99
     assert L.ld_fly_pid_f64_device(C.byref(p), C.byref(q), 16, 4, 16, None, None) == -1
