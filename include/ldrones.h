@@ -155,8 +155,11 @@ int ld_fly_mlp_f64_device(const ld_params* params, const double* genomes, int64_
                           int64_t* work_counter, void* stream);
 
 /* Same computation with HOST buffers: copies in, runs, copies out, synchronises.
- * This is the call the reference-facing plugin makes (bench e2e). Chunks the
- * population so H2D copies overlap the kernel. */
+ * This is the call the reference-facing plugin makes (bench e2e).  One persistent
+ * launch per <= 4 Mi drones that starts on an empty genome matrix: the chunked H2D
+ * copies are queued first and raise an arrival counter the kernel's work queue
+ * waits on, so lanes start flying as their rows land (pinned host memory overlaps
+ * fully; pageable memory is staged by the driver and overlaps less). */
 int ld_fly_mlp_f64_host(const ld_params* params, const double* genomes, int64_t n,
                         ld_record* records, double* final_state);
 
