@@ -20,7 +20,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 G = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 genomes = bench.population("survivors", n)
 for mode in ("block", "step", "block", "step"):
-    ev = GpuEvolution(genomes, seed=2026, timesteps=2000)
+    ev = GpuEvolution(genomes, seed=2026, timesteps=2000, **({"slice_steps": int(os.environ["LD_SLICE_STEPS"])} if "LD_SLICE_STEPS" in os.environ else {}))
     ev.step()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
