@@ -31,15 +31,16 @@ sys.path.insert(0, ROOT)
 METRIC = "drone-steps/sec (dynamics+brain+reward)"
 UNIT = "drone-steps/s"
 FLOP_PER_STEP = 850.0  # SURVEY.md §8d algorithmic work per drone-step (FMA = 2)
-FP64_INSTR_PER_STEP = 638.0  # executed fp64-pipe instructions per drone-step (ncu source counters, profiles/r01_g_*)
+FP64_INSTR_PER_STEP = 638.0  # executed fp64-pipe instructions per drone-step (ncu source counters, profiles/r01_h_*)
 GENOME_BYTES = 314 * 8
 RECORD_BYTES = 32
 # dram__bytes_read.sum + dram__bytes_write.sum of fly_mlp_f64_kernel for the default workload
-# (65,536 survivors x 2,000 steps), one `ncu --set full` capture: profiles/r01_g_fly_mlp_f64_ncu_full_summary.csv.
-# 2.18x the algorithmic bytes ON PURPOSE: the episode is flown in two segments (ld_params.slice_steps), every
-# drone is parked once (256 B out + in) and its 2,512-B brain row is read a second time — 0.2 GB of extra
-# traffic (0.8 % of HBM peak for 7 ms) that removes the 13.5 % wave-quantisation loss of 3.46 waves.
-NCU_TRAFFIC_DEFAULT_WORKLOAD = 342274816 + 21697280
+# (65,536 survivors x 2,000 steps), one `ncu --set full` capture: profiles/r01_h_fly_mlp_f64_ncu_full_summary.csv.
+# 3.4x the algorithmic bytes ON PURPOSE: the episode is flown in three segments (ld_params.slice_steps, boundaries
+# at 500 and 1,500 steps), every drone is parked twice (256 B out + in) and its 2,512-B brain row is read three
+# times — 0.4 GB of extra traffic (1.2 % of HBM peak for 7 ms) that removes the 13.5 % wave-quantisation loss of
+# 3.46 waves and starts the lanes of a streamed launch evenly.
+NCU_TRAFFIC_DEFAULT_WORKLOAD = 521041664 + 39618816
 
 
 def population(kind, n, seed=2026):
@@ -365,15 +366,15 @@ def main():
                          "pipe_utilisation": steps_per_launch * FP64_INSTR_PER_STEP / (kernel_ms * 1e-3) / (tf.value * 1e12 / 2.0),
                          "note": "achieved = active drone-steps per launch x 850 algorithmic flop / kernel time; "
                                  "pipe_utilisation = executed fp64-pipe thread-instructions (ncu: 418 DFMA + 116 DMUL + 83 DADD "
-                                 "+ 21 DSETP per drone-step, profiles/r01_g_*) / measured DFMA issue peak; the co-limiter is "
+                                 "+ 21 DSETP per drone-step, profiles/r01_h_*) / measured DFMA issue peak; the co-limiter is "
                                  "dependency latency with one warp per SM sub-partition (brain capacity), DESIGN.md 4"},
             "hbm_roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved_gbs / peaks["hbm_gbs"], "algorithmic_bytes": alg_bytes,
                              "traffic": NCU_TRAFFIC_DEFAULT_WORKLOAD if (D, H, args.population) == (65536, 2000, "survivors") else None,
                              "peak_source": peaks_src,
                              "note": "compute-bound by construction: 2,544 algorithmic bytes per 2,000-step episode; the measured traffic is "
-                                     "2.18x that on purpose (episode flown in two segments: brain row read twice, drone parked once) "
-                                     "— 0.2 GB of idle HBM bandwidth traded for the 13.5 % wave-quantisation loss, DESIGN.md 4"},
+                                     "3.4x that on purpose (episode flown in three segments: brain row read three times, drone parked "
+                                     "twice) — 0.4 GB of idle HBM bandwidth traded for the 13.5 % wave-quantisation loss, DESIGN.md 4"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": D * GENOME_BYTES * world,
                     "d2h_bytes_per_step": D * RECORD_BYTES * world, "api": "ld_fly_mlp_f64_host via fly_population_host (one persistent launch; genome rows stream in behind it)"},
             "gpu_launches": args.steps * world,

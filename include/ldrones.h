@@ -116,10 +116,13 @@ typedef struct ld_params {
     int32_t punish_time;   /* bool */
     int32_t refill_batch;  /* tuning: idle lanes per warp that trigger a queue refill; 0 = library default */
     int32_t slice_steps;   /* scheduling only, never changes results: when more drones wait than the GPU has
-                              lanes, an fp64 episode is flown in segments of this many steps and the drone goes
-                              back to the queue in between (round robin), so that a population of long-lived
-                              drones ends together instead of in whole-episode waves.  0 = library default,
-                              < 0 = off (every drone keeps its lane until its episode ends) */
+                              lanes, an fp64 episode is flown in segments and the drone goes back to the queue in
+                              between (round robin), so that long-lived drones end together instead of in
+                              whole-episode waves and short-lived ones free their lane early.
+                              > 0: equal segments of this many steps; <= -2: segments that double in length,
+                              the first one -slice_steps steps long; 0 = library default (doubling from
+                              timesteps/4 for populations of 1..16 waves); -1 = off (every drone keeps its lane
+                              until its episode ends) */
     int32_t reserved0;
 } ld_params;
 

@@ -44,10 +44,10 @@ class GpuEvolution:
         self.shard_rows = self.hi - self.lo
         slice_steps = fly_kw.pop("slice_steps", None)
         self.params = make_params(timesteps=timesteps, **fly_kw)
-        # Offspring populations mix a few long-lived drones with many that crash early; measured on B200 they fly
-        # 2-7 % faster with four segments per episode than with the library's automatic choice, which is tuned
-        # for populations where every drone survives (ld_params.slice_steps; scheduling only, results identical)
-        self.params.slice_steps = max(250, timesteps // 4) if slice_steps is None else int(slice_steps)
+        # Scheduling only (ld_params.slice_steps).  Offspring populations mix a few long-lived drones with many
+        # that crash early: always fly them in doubling segments (boundaries H/4, 3H/4), also where the library's
+        # automatic rule — which has to assume that every drone may survive — would not bother.
+        self.params.slice_steps = -max(125, timesteps // 4) if slice_steps is None else int(slice_steps)
         self.seed, self.generation = int(seed), 0
         self.hyper = dict(p_tournament=p_tournament, p_crossover=p_crossover, mutation_rate=mutation_rate, mutation_sigma=mutation_sigma)
         # best-of-run tracking lives on the device (ld_track_best_device): {score, valid}, the genome, and one

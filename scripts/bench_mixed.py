@@ -21,7 +21,7 @@ for frac in fracs:
     g = np.concatenate([G.survivors(k, rng), G.random_brains(n - k, rng)])[rng.permutation(n)]
     gt = torch.from_numpy(g).cuda()
     row = []
-    for sl in (-1, 0, 500, 250):
+    for sl in (0, 500, 250, -250, -125, -500):
         p = make_params(2000)
         p.slice_steps = sl
         rec = None

@@ -31,7 +31,9 @@ for i in range(runs):
     gt = torch.from_numpy(genomes).cuda()
     p.slice_steps = -1
     ref, _ = pop.fly_population_device(gt, p)
-    p.slice_steps = int(rng.integers(1, H + 20))
+    p.slice_steps = int(rng.integers(1, H + 20)) * (1 if rng.random() < 0.6 else -1)
+    if p.slice_steps == -1:
+        p.slice_steps = -2
     p.refill_batch = int(rng.integers(0, 33))
     if i % 3 == 0:
         out, _ = pop.fly_population_host(genomes, p)

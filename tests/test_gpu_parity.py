@@ -88,7 +88,7 @@ def test_device_api_equals_host_api(pop, gen):
     assert rec_p.tobytes() == rec_h[perm].tobytes()
 
 
-@pytest.mark.parametrize("slice_steps", [0, 64, 150, 599, 4000])
+@pytest.mark.parametrize("slice_steps", [0, 64, 150, 599, 4000, -40])
 def test_episode_segments_do_not_change_results(pop, gen, slice_steps):
     """ld_params.slice_steps is scheduling only: with more drones than lanes, drones are parked at segment
     boundaries and resumed on other lanes — records and final states stay bit-identical to the unsegmented run."""
@@ -123,7 +123,7 @@ def test_episode_segments_do_not_change_results(pop, gen, slice_steps):
     assert rec_p.tobytes() == r0.tobytes()
 
 
-@pytest.mark.parametrize("extra,slice_steps,batch", [(1, 7, 1), (33, 13, 32), (5000, 1, 0)])
+@pytest.mark.parametrize("extra,slice_steps,batch", [(1, 7, 1), (33, 13, 32), (5000, 1, 0), (77, -3, 5)])
 def test_episode_segments_stress(pop, gen, extra, slice_steps, batch):
     """Tiny segments (down to one step), a population just above one wave, extreme refill batches."""
     import torch
