@@ -6,4 +6,4 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29661 bench.py --gpus $N --drones-per-gpu $((1048576/N)) --steps 5 --generations 10 > gpurun_out/p2p_config4_n$N.json 2> gpurun_out/p2p_config4.err
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29662 scripts/evolve_b200.py --drones 1048576 --generations 100 --timesteps 2000 2>&1 | grep -v OMP | tail -3 > gpurun_out/p2p_config5_n$N.txt
 cat gpurun_out/p2p_config5_n$N.txt
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29663 scripts/test_p2p_evolution.py 2>&1 | grep "p2p =="
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29663 scripts/p2p_evolution_check.py 2>&1 | grep "p2p =="

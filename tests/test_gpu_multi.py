@@ -26,7 +26,7 @@ def _torchrun(args, port):
 def test_p2p_evolution_matches_replicated():
     if _gpus() < 2:
         pytest.skip("needs 2 GPUs")
-    r = _torchrun(["scripts/test_p2p_evolution.py"], 29541)
+    r = _torchrun(["scripts/p2p_evolution_check.py"], 29541)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "p2p == replicated: True" in r.stdout
 
