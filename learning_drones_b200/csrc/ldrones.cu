@@ -926,10 +926,8 @@ ga_step_kernel(const __grid_constant__ ld_ga_params ga, const double* __restrict
         double* __restrict__ cb = children + (c + 1 - lo) * LD_GENOME_LEN;
         // Pass 1 — copy with crossover.  Each lane handles groups of 4 consecutive genes (32 B per row, 16-B
         // vector accesses; rows are 16-B aligned).  One Philox block per child and group gives the four
-        // Bernoulli(mutation_rate) decisions (32-bit resolution); mutated genes are only LISTED here.
+        // `random_sample() < mutation_rate` decisions (uniform = word * 2^-32); mutated genes are only LISTED here.
         constexpr int kGroups = (LD_GENOME_LEN + 3) / 4; // 79, the last group has 2 genes
-        const uint32_t thr = (uint32_t)fmin(ga.mutation_rate * 4294967296.0, 4294967295.0);
-        const bool always = ga.mutation_rate >= 1.0;
         unsigned short* list = mut_list[threadIdx.x >> 5];
         int n_mut = 0; // warp-uniform
         for (int q0 = 0; q0 < kGroups; q0 += 32) {
@@ -957,7 +955,7 @@ ga_step_kernel(const __grid_constant__ ld_ga_params ga, const double* __restrict
             for (int w = 0; w < 2; ++w) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const bool hit = j < cnt && (always || m[w].v[j] < thr);
+                    const bool hit = j < cnt && ((double)m[w].v[j] * 0x1.0p-32 < ga.mutation_rate); // random_sample() < rate
                     const unsigned vote = __ballot_sync(0xffffffffu, hit);
                     if (hit) list[n_mut + __popc(vote & ((1u << lane) - 1u))] = (unsigned short)(((g0 + j) << 1) | w);
                     n_mut += __popc(vote);

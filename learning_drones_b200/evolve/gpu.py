@@ -14,6 +14,7 @@ Philox stream, not numpy's global MT19937, and there is no jsonpick
 `best_genome()` / `learning_drones_b200.drone.drone.Drone.controller.set_genome`.
 """
 import ctypes as C
+import warnings
 
 import numpy as np
 
@@ -57,15 +58,22 @@ class GpuEvolution:
         self._stats = torch.empty(5, dtype=torch.int64, device=self.device)
         self._history = torch.zeros((0, 7), dtype=torch.int64, device=self.device)
         self.records = None  # fitness records of the generation flown last (whole population)
-        self.p2p = False
+        # How the GA step reaches its parents — reported, never silent (bench.py prints it):
+        #   "single"     one rank, the whole population in this GPU's memory
+        #   "p2p"        shards in symmetric memory, parents loaded over NVLink inside the GA kernel
+        #   "replicated" genome matrix replicated, child shards all-gathered with NCCL
+        self.p2p, self.p2p_error = False, None
         if self.world > 1 and p2p is not False:
             try:
                 self._setup_p2p(g)
                 self.p2p = True
-            except Exception as e:  # symmetric memory not available on this system
+            except (RuntimeError, ImportError, AttributeError, NotImplementedError) as e:
+                # torch symmetric memory cannot be set up on this system (no NVLink peer access, old torch)
                 if p2p is True:
                     raise
-                self._p2p_error = repr(e)
+                self.p2p_error = repr(e)
+                warnings.warn(f"GpuEvolution: peer-memory GA step unavailable, using the replicated mode: {e!r}", RuntimeWarning)
+        self.ga_mode = "single" if self.world == 1 else ("p2p" if self.p2p else "replicated")
         if not self.p2p:
             self.population = g.to(self.device, dtype=torch.float64).contiguous().clone()
             self.next_population = torch.empty_like(self.population)
@@ -163,3 +171,67 @@ class GpuEvolution:
         out = torch.empty((self.n, GENOME_LEN), dtype=torch.float64, device=self.device)
         self.dist.all_gather_into_tensor(out, self._bufs[self._cur].clone())
         return out.cpu().numpy()
+
+
+class LocalShardedEvolution:
+    """The sharded loop of GpuEvolution for `world` shards that all live on ONE GPU: every shard has its own
+    buffers, the GA step and the best tracking address parents through an ld_peer_table exactly as they do over
+    NVLink (ld_ga_step_p2p_device, ld_track_best_device(peers)).  Same results as GpuEvolution on one rank — which
+    is what tests/test_gpu_ga.py checks, so the peer-memory code path is exercised on a single-GPU box too."""
+
+    ga_mode = "p2p-local"
+
+    def __init__(self, genomes, world: int, seed: int = 0, timesteps: int = 2500, mutation_rate: float = 0.05, p_tournament: float = 0.6,
+                 p_crossover: float = 0.05, mutation_sigma: float = 0.3, device=None, **fly_kw):
+        import torch
+
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        g = torch.as_tensor(np.ascontiguousarray(genomes, dtype=np.float64)) if not torch.is_tensor(genomes) else genomes
+        self.n, self.world = g.shape[0], int(world)
+        if g.dim() != 2 or g.shape[1] != GENOME_LEN or self.n % (2 * self.world) != 0:
+            raise ValueError(f"genomes must have shape (n, {GENOME_LEN}) with n a multiple of 2 x world")
+        self.shard_rows = self.n // self.world
+        slice_steps = fly_kw.pop("slice_steps", None)
+        self.params = make_params(timesteps=timesteps, **fly_kw)
+        self.params.slice_steps = -max(125, timesteps // 4) if slice_steps is None else int(slice_steps)
+        self.seed, self.generation = int(seed), 0
+        self.hyper = dict(p_tournament=p_tournament, p_crossover=p_crossover, mutation_rate=mutation_rate, mutation_sigma=mutation_sigma)
+        rows = self.shard_rows
+        self._bufs = [[g[r * rows:(r + 1) * rows].to(self.device, dtype=torch.float64).contiguous().clone() for r in range(self.world)],
+                      [torch.empty((rows, GENOME_LEN), dtype=torch.float64, device=self.device) for _ in range(self.world)]]
+        self._tables = [make_peer_table([t.data_ptr() for t in bufs], rows) for bufs in self._bufs]
+        self._cur = 0
+        self._best = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.global_best_genome = torch.empty(GENOME_LEN, dtype=torch.float64, device=self.device)
+        self._stats = torch.empty(5, dtype=torch.int64, device=self.device)
+        self.records = torch.empty((self.n, 4), dtype=torch.int64, device=self.device)
+
+    def run(self, n_generations: int):
+        torch = self.torch
+        L = _lib.load()
+        history = torch.zeros((n_generations, 7), dtype=torch.int64, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rows = self.shard_rows
+        with torch.cuda.device(self.device):
+            for g in range(n_generations):
+                cur, nxt, table = self._bufs[self._cur], self._bufs[1 - self._cur], self._tables[self._cur]
+                for r in range(self.world):  # "all-gather": every shard's records land in population order
+                    fly_population_device(cur[r], self.params, records=self.records[r * rows:(r + 1) * rows])
+                reduce_records_device(self.records, self._stats)
+                ga = make_ga_params(self.seed, self.generation, **self.hyper)
+                _lib.check(L.ld_track_best_device(self._stats.data_ptr(), None, C.byref(table), self.generation, self._best.data_ptr(),
+                                                  self.global_best_genome.data_ptr(), history[g].data_ptr(), stream))
+                for r in range(self.world):
+                    _lib.check(L.ld_ga_step_p2p_device(C.byref(ga), C.byref(table), self.records.data_ptr(), self.n, nxt[r].data_ptr(),
+                                                       r * rows, (r + 1) * rows, stream))
+                nxt[0][0].copy_(self.global_best_genome)  # elitism, evolution.py:105-107
+                self._cur = 1 - self._cur
+                self.generation += 1
+        return [GpuEvolution._history_dict(r) for r in history.cpu().tolist()]
+
+    def best_genome(self) -> np.ndarray:
+        return self.global_best_genome.cpu().numpy()
+
+    def gather_population(self) -> np.ndarray:
+        return self.torch.cat(self._bufs[self._cur]).cpu().numpy()

@@ -504,17 +504,15 @@ int ld_oracle_ga_step(const ld_ga_params* ga, const double* parents, const int64
                 }
             }
         }
-        /* drone.py:167-172 — Bernoulli(rate) per gene from one Philox block per group of 4 genes (32-bit
-         * resolution), a second block per mutated gene for its Box-Muller N(0, sigma) draw */
-        double thr_d = ga->mutation_rate * 4294967296.0;
-        uint32_t thr = thr_d >= 4294967295.0 ? 4294967295u : (uint32_t)thr_d;
-        int always = ga->mutation_rate >= 1.0;
+        /* drone.py:167-172 — per gene `random_sample() < rate` with the uniform v * 2^-32 taken from one Philox
+         * block per group of 4 genes, a second block per mutated gene for its Box-Muller N(0, sigma) draw.
+         * Pinned to the reference by draw replay: oracle/gen_ga_replay.py, tests/golden/ga_reference_replay.npz */
         for (int w = 0; w < 2; ++w) {
             int nm = 0;
             od_u4 m = {{0, 0, 0, 0}};
             for (int g = 0; g < LD_GENOME_LEN; ++g) {
                 if (g % 4 == 0) m = philox4x32_10((uint32_t)(c + w), (uint32_t)(g / 4), OD_STREAM_MUTATE, gen, k0, k1);
-                if (always || m.v[g % 4] < thr) {
+                if ((double)m.v[g % 4] * 0x1.0p-32 < ga->mutation_rate) { /* random_sample() < mutation_rate, 32-bit uniform */
                     od_u4 x = philox4x32_10((uint32_t)(c + w), (uint32_t)g, OD_STREAM_NOISE, gen, k0, k1);
                     double u1 = ((double)x.v[0] + 0.5) * 0x1.0p-32, u2 = ((double)x.v[1] + 0.5) * 0x1.0p-32;
                     double z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2); /* Box-Muller */

@@ -121,3 +121,124 @@ def test_gpu_evolution_loop():
         if best is None or h["best_score"] > best:
             best, best_row = h["best_score"], pop_before[h["best_index"]].cpu().numpy()
         assert h["global_best_score"] == best and np.array_equal(ev4.best_genome(), best_row)
+
+
+# ---- pinned to the reference by draw replay (oracle/gen_ga_replay.py) ---------------------------------
+from test_ga_oracle import REPLAY_CASES, replay_case  # noqa: E402
+
+
+@pytest.mark.parametrize("name", REPLAY_CASES)
+def test_ga_kernel_reproduces_reference_children(golden, name):
+    """The CUDA GA step + device-side best tracking + elitism against children produced by the REFERENCE's own
+    selection_and_crossover / reset / mutate / elitism code fed with the library's draws."""
+    import torch
+
+    from learning_drones_b200 import _lib
+    from learning_drones_b200.population import reduce_records_device
+
+    L = _lib.load()
+    g, ga = replay_case(golden, name)
+    parents, rewards = g[f"{name}_parents"], g[f"{name}_rewards"]
+    n = parents.shape[0]
+    want = g[f"{name}_children_before_elitism"]
+    got = gpu_ga(ga, parents, rewards)
+    # a gene the reference did not mutate is a bit-exact copy of a parent gene; mutated genes carry CUDA's log/cos
+    is_copy = np.zeros_like(want, dtype=bool)
+    for c in range(n):
+        is_copy[c] = (want[c][None, :] == parents).any(axis=0)
+    assert np.array_equal(got[is_copy], want[is_copy])
+    assert np.abs(got - want).max() < 1e-12 and (~is_copy).sum() > 0
+    # evolution.py:77-107 on the device: arg-max, best-so-far (possibly carried in from an earlier generation), slot 0
+    rec = np.zeros(n, dtype=RECORD_DTYPE)
+    rec["reward"] = rewards
+    rt = torch.from_numpy(rec.view(np.int64).reshape(-1, 4).copy()).cuda()
+    pt = torch.from_numpy(parents).cuda()
+    carried = int(g[f"{name}_carried_score"])
+    best2 = torch.tensor([carried, 1] if carried > -(2 ** 61) else [0, 0], dtype=torch.int64, device="cuda")
+    best_genome = torch.from_numpy(g[f"{name}_carried_genome"].copy()).cuda()
+    hist = torch.zeros(7, dtype=torch.int64, device="cuda")
+    stats = reduce_records_device(rt)
+    _lib.check(L.ld_track_best_device(stats.data_ptr(), pt.data_ptr(), None, int(ga.generation), best2.data_ptr(), best_genome.data_ptr(),
+                                      hist.data_ptr(), None))
+    kids = torch.from_numpy(got).cuda()
+    kids[0].copy_(best_genome)
+    torch.cuda.synchronize()
+    assert hist.tolist()[2] == int(g[f"{name}_best_index"]) and best2.tolist() == [int(g[f"{name}_global_best_score"]), 1]
+    assert np.array_equal(best_genome.cpu().numpy(), g[f"{name}_global_best_genome"])
+    final = kids.cpu().numpy()
+    assert np.array_equal(final[0], g[f"{name}_children"][0])
+    assert np.abs(final - g[f"{name}_children"]).max() < 1e-12
+
+
+# ---- the peer-memory instantiation (ga_step_kernel<true>, track_best over a peer table) on ONE GPU ----
+@pytest.mark.parametrize("world,separate", [(2, False), (4, True), (8, False), (8, True)])
+def test_ga_p2p_kernel_with_local_peer_table(world, separate):
+    """ld_ga_step_p2p_device / ld_track_best_device(peers) address parents through a table of per-rank shard
+    pointers (NVLink peer mappings on a multi-GPU box).  Here the "peers" are shards in this GPU's own memory —
+    slices of one buffer, or separately allocated tensors — so the P2P code path runs wherever the tests run;
+    every rank's children must be bit-identical to the single-buffer kernel's."""
+    import torch
+
+    from learning_drones_b200 import _lib
+    from learning_drones_b200._abi import make_peer_table
+    from learning_drones_b200.population import reduce_records_device
+
+    L = _lib.load()
+    rows = 250
+    n = world * rows
+    rng = np.random.default_rng(world)
+    parents = rng.standard_normal((n, GENOME_LEN))
+    rewards = rng.integers(-5000, 4000, size=n)
+    ga = make_ga_params(seed=0xABCDEF987, generation=11, p_crossover=0.3, mutation_rate=0.05)
+    want = gpu_ga(ga, parents, rewards)
+    rec = np.zeros(n, dtype=RECORD_DTYPE)
+    rec["reward"] = rewards
+    rt = torch.from_numpy(rec.view(np.int64).reshape(-1, 4).copy()).cuda()
+    pt = torch.from_numpy(parents).cuda()
+    if separate:
+        shards = [pt[r * rows:(r + 1) * rows].clone() for r in reversed(range(world))][::-1]  # allocation order != rank order
+    else:
+        shards = [pt[r * rows:(r + 1) * rows] for r in range(world)]
+    table = make_peer_table([s.data_ptr() for s in shards], rows)
+    for r in range(world):
+        out = torch.zeros((rows, GENOME_LEN), dtype=torch.float64, device="cuda")
+        _lib.check(L.ld_ga_step_p2p_device(C.byref(ga), C.byref(table), rt.data_ptr(), n, out.data_ptr(), r * rows, (r + 1) * rows, None))
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), want[r * rows:(r + 1) * rows]), f"rank {r}"
+    # best tracking through the peer table == through the whole population
+    stats = reduce_records_device(rt)
+    outs = []
+    for peers in (None, table):
+        best2 = torch.zeros(2, dtype=torch.int64, device="cuda")
+        best_genome = torch.zeros(GENOME_LEN, dtype=torch.float64, device="cuda")
+        hist = torch.zeros(7, dtype=torch.int64, device="cuda")
+        _lib.check(L.ld_track_best_device(stats.data_ptr(), pt.data_ptr() if peers is None else None,
+                                          None if peers is None else C.byref(peers), 3, best2.data_ptr(), best_genome.data_ptr(),
+                                          hist.data_ptr(), None))
+        torch.cuda.synchronize()
+        outs.append((best2.tolist(), best_genome.cpu().numpy(), hist.tolist()))
+    assert outs[0][0] == outs[1][0] == [int(rewards.max()), 1] and outs[0][2] == outs[1][2]
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][1], parents[int(np.argmax(rewards))])
+    # argument validation of the peer form
+    bad = make_peer_table([s.data_ptr() for s in shards], rows + 2)
+    out = torch.zeros((rows, GENOME_LEN), dtype=torch.float64, device="cuda")
+    assert L.ld_ga_step_p2p_device(C.byref(ga), C.byref(bad), rt.data_ptr(), n, out.data_ptr(), 0, rows, None) != 0
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_evolution_loop_on_one_gpu(world):
+    """GpuEvolution's sharded loop (fly shard -> gather records -> track best over peers -> P2P GA step -> elitism
+    on rank 0) run for `world` emulated ranks on one GPU must give the single-rank loop's populations."""
+    from oracle import gen_golden as G
+
+    from learning_drones_b200.evolve.gpu import GpuEvolution, LocalShardedEvolution
+
+    rng = np.random.default_rng(4)
+    genomes = G.random_brains(world * 256, rng)
+    a = GpuEvolution(genomes, seed=9, timesteps=400)
+    b = LocalShardedEvolution(genomes, world=world, seed=9, timesteps=400)
+    assert a.ga_mode == "single" and b.ga_mode == "p2p-local"
+    ha, hb = a.run(4), b.run(4)
+    assert ha == hb
+    assert np.array_equal(a.gather_population(), b.gather_population())
+    assert np.array_equal(a.best_genome(), b.best_genome())
