@@ -239,7 +239,7 @@ def main():
     pinned = torch.from_numpy(np.ascontiguousarray(host_genomes)).pin_memory()
     genomes = pinned.to(dev)
     records = torch.empty((D, 4), dtype=torch.int64, device=dev)
-    counter = torch.empty(1, dtype=torch.int64, device=dev)
+    counter = torch.empty(2, dtype=torch.int64, device=dev)  # queue head, error flag
 
     prec = args.precision
     if prec != "f64":

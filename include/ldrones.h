@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define LD_ABI_VERSION 2
+#define LD_ABI_VERSION 3
 
 /* brain shape fixed by drone/drone.py:65 : NeuralNetwork({1:10, 2:10, 3:4}), n_inputs=15 */
 #define LD_N_IN 15
@@ -57,9 +57,13 @@ typedef enum ld_status {
     LD_OK = 0,
     LD_ERR_INVALID_ARG = -1, /* NULL pointer, negative size, bad params */
     LD_ERR_CUDA = -2,        /* a CUDA runtime call failed; see ld_last_error() */
-    LD_ERR_NO_DEVICE = -3,   /* no usable sm_100 device */
-    LD_ERR_NCCL = -4
+    LD_ERR_NO_DEVICE = -3    /* no usable sm_100 device */
 } ld_status;
+/* There is no collective entry point in this ABI: the one exchange step of the path, the all-gather of the 32-byte
+ * fitness records, is torch.distributed's NCCL all-gather on the caller's side
+ * (learning_drones_b200/distributed.py); the SURVEY §8b sketch's `ld_allgather_records` is struck.  The irregular
+ * exchange — the GA step's parent fetch — IS in the library, fused into the kernel over peer memory
+ * (ld_ga_step_p2p_device). */
 
 /* status bits of ld_record.status */
 #define LD_STATUS_CRASHED 1   /* drone/drone.py:150-154 */
@@ -150,8 +154,10 @@ int64_t ld_wave_size(void);
  * genomes      [n][LD_GENOME_LEN] doubles
  * records      [n] ld_record                        (written)
  * final_state  [n][LD_STATE_LEN] doubles or NULL    (written if not NULL)
- * work_counter one int64 of scratch device memory used as the refill queue head
- *              (the call zeroes it itself, stream-ordered)
+ * work_counter TWO int64 of scratch device memory: [0] is the work-queue head, [1] an error flag.  The call
+ *              zeroes both itself (stream-ordered); after the launch has completed, work_counter[1] != 0 means that
+ *              a warp gave up waiting for its work queue (20 s without progress — never in a healthy run) and the
+ *              records are incomplete.  The *_host entry points check it and return LD_ERR_CUDA.
  */
 int ld_fly_mlp_f64_device(const ld_params* params, const double* genomes, int64_t n,
                           ld_record* records, double* final_state,
@@ -165,6 +171,17 @@ int ld_fly_mlp_f64_device(const ld_params* params, const double* genomes, int64_
  * fully; pageable memory is staged by the driver and overlaps less). */
 int ld_fly_mlp_f64_host(const ld_params* params, const double* genomes, int64_t n,
                         ld_record* records, double* final_state);
+
+/* The same with a per-drone START state: init_state [n][LD_STATE_LEN] rows (pos vel angle angle_vel acc_current
+ * acc_last thrust; acc_last is ignored) replace ld_params.init_*.  This is fly() on Drones that are not in the reset
+ * state — the reference continues from whatever position / velocity / angle / thrust / sensor accelerations the Drone
+ * holds (flight/__init__.py:35-39, drone/drone.py:20-76 constructor arguments).  Counters start at 0: the reference
+ * accumulates reward, coins and flight_time on top of the Drone's previous values, which is an integer addition the
+ * caller does (learning_drones_b200/flight/__init__.py).  init_state == NULL is ld_fly_mlp_f64_{host,device}. */
+int ld_fly_mlp_f64_from_host(const ld_params* params, const double* genomes, const double* init_state, int64_t n,
+                             ld_record* records, double* final_state);
+int ld_fly_mlp_f64_from_device(const ld_params* params, const double* genomes, const double* init_state, int64_t n,
+                               ld_record* records, double* final_state, int64_t* work_counter, void* stream);
 
 /* fp32 FAST MODE: same call contract and the same fp64 genome matrix / record
  * layout, but state, brain and arithmetic are float32 on the device.  The dynamics are chaotic:
@@ -191,6 +208,18 @@ int ld_fly_mlp_f64_trace_device(const ld_params* params, const double* genome,
  * Host buffers; same device arithmetic as the episode kernel. */
 int ld_drone_step_host(const ld_params* params, int what, const double* genomes, double* state, const double* coin,
                        int32_t* flags, int64_t n);
+
+/* NeuralNetwork.feed_forward for ANY layer_spec (evolve/brain.py:10,41-54; the reference's own default is
+ * {1: 8, 2: 10, 3: 4}): layer_sizes[0..n_layers] = inputs, then neurons per layer (<= 8 layers, widths <= 64);
+ * weights = per layer (n_out, n_in + 1) row-major, bias LAST, layer after layer; row i of inputs [n][sizes[0]] goes
+ * through the brain at weights + i * weights_stride (weights_stride == 0: one brain for every row); hidden ReLU,
+ * output sigmoid(beta).  Same device arithmetic as the episode kernel (k-ordered fma chains), so the Drone's
+ * 15-10-10-4 shape reproduces the episode kernel's thrust bit for bit.  Host buffers. */
+int ld_brain_forward_host(const int32_t* layer_sizes, int32_t n_layers, const double* weights, int64_t weights_stride,
+                          const double* inputs, int64_t n, double* outputs, double sigmoid_beta);
+/* NeuralNetwork._relu / relu (kind 0: out = x < a ? 0.0 : b * x, brain.py:26-35) and sigmoid (kind 1:
+ * out = 1 / (exp(-a x) + 1), brain.py:37-39) on the device.  Host buffers. */
+int ld_activation_host(int kind, const double* x, int64_t n, double* out, double a, double b);
 
 /* ---- PID-controlled episode (second controller mode) ------------
  * The main loop of flight/collect_coins.py:278-364 for a batch of PID gain sets: per step
@@ -291,7 +320,7 @@ int ld_measure_fp64_peak(double* tflops_out, double* dfma_per_clk_per_sm_out);
  * fn 0: out0=sin(x) out1=cos(x) | 1: out0=exp(x) | 2: out0=1/(exp(-0.4x)+1) | 3: out0=x/y out1=1/y */
 int ld_debug_math_device(int fn, const double* x, const double* y, double* out0, double* out1, int64_t n, void* stream);
 
-/* frees the device workspace that ld_fly_mlp_f64_host keeps between calls (per host thread) */
+/* frees the device workspaces that the *_host entry points keep between calls (per host thread) */
 void ld_release_workspace(void);
 
 #ifdef __cplusplus

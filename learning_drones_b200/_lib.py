@@ -18,6 +18,10 @@ EXPORTS = (
     "ld_wave_size",
     "ld_fly_mlp_f64_device",
     "ld_fly_mlp_f64_host",
+    "ld_fly_mlp_f64_from_host",
+    "ld_fly_mlp_f64_from_device",
+    "ld_brain_forward_host",
+    "ld_activation_host",
     "ld_fly_mlp_f64_trace_device",
     "ld_reduce_records_device",
     "ld_release_workspace",
@@ -65,6 +69,14 @@ def load():
     L.ld_fly_mlp_f64_device.restype = C.c_int
     L.ld_fly_mlp_f64_host.argtypes = [C.POINTER(LdParams), dp, i64, vp, dp]
     L.ld_fly_mlp_f64_host.restype = C.c_int
+    L.ld_fly_mlp_f64_from_host.argtypes = [C.POINTER(LdParams), dp, dp, i64, vp, dp]
+    L.ld_fly_mlp_f64_from_host.restype = C.c_int
+    L.ld_fly_mlp_f64_from_device.argtypes = [C.POINTER(LdParams), dp, dp, i64, vp, dp, vp, vp]
+    L.ld_fly_mlp_f64_from_device.restype = C.c_int
+    L.ld_brain_forward_host.argtypes = [C.POINTER(C.c_int32), C.c_int32, dp, i64, dp, i64, dp, C.c_double]
+    L.ld_brain_forward_host.restype = C.c_int
+    L.ld_activation_host.argtypes = [C.c_int, dp, i64, dp, C.c_double, C.c_double]
+    L.ld_activation_host.restype = C.c_int
     L.ld_fly_mlp_f32_device.argtypes = [C.POINTER(LdParams), dp, i64, vp, dp, vp, vp]
     L.ld_fly_mlp_f32_device.restype = C.c_int
     L.ld_fly_mlp_f32_host.argtypes = [C.POINTER(LdParams), dp, i64, vp, dp]

@@ -138,8 +138,14 @@ struct Sched {
     // host-buffer entry point: genome rows [0, *arrived) are in HBM, the copy engine raises the count
     // after every chunk while the kernel is already flying the first ones (NULL = everything is there)
     const unsigned long long* arrived;
-    int* error;               // set to 1 if a lane gave up waiting (kWaitLimitNs); may be NULL
+    int* error;               // set to 1 if a warp gave up waiting (kWaitLimitNs); never NULL (work_counter[1] of the device API)
+    // optional per-drone start: [n][LD_STATE_LEN] rows (pos vel angle angle_vel acc_current acc_last thrust) that
+    // replace ld_params.init_* — fly() on Drones that are not in the reset state (flight/__init__.py:35-39)
+    const double* init_state;
 };
+// a warp that has had nothing to fly and nothing become ready for this long gives up (never in a healthy run: it
+// turns a lost queue entry into an error instead of a hung GPU).  Measured from the moment the warp began to wait
+// without progress, so long launches, debuggers and time-sliced GPUs do not trip it.
 constexpr unsigned long long kWaitLimitNs = 20ull * 1000 * 1000 * 1000;
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -204,6 +210,21 @@ __device__ __forceinline__ void unpark_drone(Drone& d, const double* __restrict_
     d.unstable = __double2hiint(b);
     d.coin_value = __double2loint(c);
     d.status = __double2hiint(c);
+}
+
+// Drone attributes + Sensor accelerations as fly() finds them on a Drone that is not freshly reset
+__device__ __forceinline__ void load_start_state(Drone& d, const double* __restrict__ row) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        d.x[i] = __ldg(row + i);
+        d.v[i] = __ldg(row + 3 + i);
+        d.x[3 + i] = __ldg(row + 6 + i);
+        d.v[3 + i] = __ldg(row + 9 + i);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) d.acc[i] = __ldg(row + 12 + i);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d.thrust[i] = __ldg(row + 24 + i);
 }
 
 __device__ __forceinline__ void write_state(const Drone& d, const double* a_last, double* row) {
@@ -388,7 +409,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
     const long long n_slots = n + q.cap;
     const int batch = p.refill_batch > 0 ? p.refill_batch : kRefillBatch;
 
-    const unsigned long long t_start = globaltimer_ns();
+    unsigned long long wait_since = 0; // 0 = the warp is not waiting (warp-uniform)
 
     Drone d;
     drone_reset(p, d);
@@ -433,6 +454,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
         if (__any_sync(0xffffffffu, drained)) more = false;
         // ---- stage the brains of the lanes that got a drone ------------------------------------------
         if (__any_sync(0xffffffffu, ready)) {
+            wait_since = 0; // progress
             const double* __restrict__ row = genomes + who * LD_GENOME_LEN;
             if (ready) {
                 // pull the 2512-B row into L1 with 20 independent loads; the gathers below then hit
@@ -450,7 +472,10 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
                 idx = who;
                 slot = -1;
                 if (resume) unpark_drone(d, q.park + who * kParkDoubles);
-                else drone_reset(p, d);
+                else {
+                    drone_reset(p, d);
+                    if (q.init_state) load_start_state(d, q.init_state + who * LD_STATE_LEN);
+                }
                 t = d.flight_time;
                 t_end = min(H, q.growth * t + q.slice);
             }
@@ -465,8 +490,10 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             if (pending == 0u && !more) break;
             if (pending != 0u) { // wait for rows to arrive, for a drone to be parked, or for the last one to land
                 __nanosleep(500);
-                if (globaltimer_ns() - t_start > kWaitLimitNs) { // never in a healthy run: do not hang the GPU
-                    if (q.error) *q.error = 1;
+                const unsigned long long now = globaltimer_ns();
+                if (wait_since == 0) wait_since = now;
+                else if (now - wait_since > kWaitLimitNs) {
+                    *q.error = 1; // reported by the host entry points and through work_counter[1] of the device API
                     slot = -1;
                     more = false;
                 }
@@ -486,6 +513,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
         // ---- hot loop: timesteps of flight/__init__.py:39-93 until some lane's segment ends ---------
         // `live` cannot change inside: lanes only leave (publish / park) or join (stage) outside of it.
         // Lanes that wait for their slot count kPollSteps steps and then have it looked at again.
+        wait_since = 0; // some lane of the warp is flying
         const bool live = idx >= 0;
         const bool counting = live || slot >= 0;
         if (!live) {
@@ -1233,13 +1261,14 @@ int auto_first_segment(long long n, long long lanes, int H) {
     return (H + 3) / 4;
 }
 
+// work_counter: int64[2] of device scratch — [0] queue head, [1] error flag (raised if a warp gave up waiting)
 int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* records, double* final_state,
                int64_t* work_counter, double* trace, cudaStream_t s, bool f32 = false,
-               const unsigned long long* arrived = nullptr, int* error = nullptr) {
+               const unsigned long long* arrived = nullptr, const double* init_state = nullptr) {
     int rc = ensure_device();
     if (rc) return rc;
     if (n == 0) return LD_OK;
-    LD_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(int64_t), s));
+    LD_CUDA(cudaMemsetAsync(work_counter, 0, 2 * sizeof(int64_t), s));
     if (f32) {
         long long ctas = (n + ldf::kThreads - 1) / ldf::kThreads;
         if (ctas > g_dev.sms) ctas = g_dev.sms;
@@ -1265,7 +1294,8 @@ int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* 
     q.head = reinterpret_cast<unsigned long long*>(work_counter);
     q.slice = H > 1 ? H : 1;
     q.arrived = arrived;
-    q.error = error;
+    q.error = reinterpret_cast<int*>(work_counter + 1);
+    q.init_state = init_state;
     // slice_steps > 0: equal segments; <= -2: segments that double in length, the first one -slice_steps long;
     // 0: automatic (doubling from H/4 when it pays); -1: off
     const bool doubling = p->slice_steps <= -2 || p->slice_steps == 0;
@@ -1348,7 +1378,7 @@ int ws_reserve(size_t chunk, bool want_state) {
         if (want_state) LD_CUDA(cudaMalloc(&g_ws.state[i], chunk * LD_STATE_LEN * sizeof(double)));
         LD_CUDA(cudaStreamCreateWithFlags(&g_ws.streams[i], cudaStreamNonBlocking));
     }
-    LD_CUDA(cudaMalloc((void**)&g_ws.counters, kHostStreams * sizeof(int64_t)));
+    LD_CUDA(cudaMalloc((void**)&g_ws.counters, 2 * kHostStreams * sizeof(int64_t)));
     g_ws.device = dev;
     g_ws.cap_drones = chunk;
     g_ws.cap_state = want_state;
@@ -1367,10 +1397,11 @@ struct StreamWs {
     double* genomes = nullptr;
     ld_record* records = nullptr;
     double* state = nullptr;
+    double* init = nullptr;
     unsigned long long* ctl = nullptr;      // [0] arrived, [1] queue head, [2] error flag
     unsigned long long* h_counts = nullptr; // pinned [kHostChunksMax]
     int* h_error = nullptr;                 // pinned
-    size_t cap_drones = 0, cap_state = 0;
+    size_t cap_drones = 0, cap_state = 0, cap_init = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t armed = nullptr;
 };
@@ -1380,6 +1411,7 @@ void sws_release() {
     if (g_sws.genomes) cudaFree(g_sws.genomes);
     if (g_sws.records) cudaFree(g_sws.records);
     if (g_sws.state) cudaFree(g_sws.state);
+    if (g_sws.init) cudaFree(g_sws.init);
     if (g_sws.ctl) cudaFree(g_sws.ctl);
     if (g_sws.h_counts) cudaFreeHost(g_sws.h_counts);
     if (g_sws.h_error) cudaFreeHost(g_sws.h_error);
@@ -1389,7 +1421,7 @@ void sws_release() {
     g_sws = StreamWs();
 }
 
-int sws_reserve(size_t drones, bool want_state) {
+int sws_reserve(size_t drones, bool want_state, bool want_init = false) {
     int dev = 0;
     LD_CUDA(cudaGetDevice(&dev));
     if (g_sws.device != dev) {
@@ -1406,8 +1438,9 @@ int sws_reserve(size_t drones, bool want_state) {
         if (g_sws.genomes) cudaFree(g_sws.genomes);
         if (g_sws.records) cudaFree(g_sws.records);
         if (g_sws.state) cudaFree(g_sws.state);
-        g_sws.genomes = nullptr; g_sws.records = nullptr; g_sws.state = nullptr;
-        g_sws.cap_drones = g_sws.cap_state = 0;
+        if (g_sws.init) cudaFree(g_sws.init);
+        g_sws.genomes = nullptr; g_sws.records = nullptr; g_sws.state = nullptr; g_sws.init = nullptr;
+        g_sws.cap_drones = g_sws.cap_state = g_sws.cap_init = 0;
         LD_CUDA(cudaMalloc((void**)&g_sws.genomes, drones * LD_GENOME_LEN * sizeof(double)));
         LD_CUDA(cudaMalloc((void**)&g_sws.records, drones * sizeof(ld_record)));
         g_sws.cap_drones = drones;
@@ -1418,11 +1451,18 @@ int sws_reserve(size_t drones, bool want_state) {
         LD_CUDA(cudaMalloc((void**)&g_sws.state, g_sws.cap_drones * LD_STATE_LEN * sizeof(double)));
         g_sws.cap_state = g_sws.cap_drones;
     }
+    if (want_init && g_sws.cap_init < drones) {
+        if (g_sws.init) cudaFree(g_sws.init);
+        g_sws.init = nullptr; g_sws.cap_init = 0;
+        LD_CUDA(cudaMalloc((void**)&g_sws.init, g_sws.cap_drones * LD_STATE_LEN * sizeof(double)));
+        g_sws.cap_init = g_sws.cap_drones;
+    }
     return LD_OK;
 }
 
 // one launch over rows [0, m) of the host matrix `genomes`
-int fly_streamed_batch(const ld_params* params, const double* genomes, int64_t m, ld_record* records, double* final_state) {
+int fly_streamed_batch(const ld_params* params, const double* genomes, const double* init_state, int64_t m, ld_record* records,
+                       double* final_state) {
     StreamWs& w = g_sws;
     const int64_t wave = (int64_t)g_dev.sms * kCtaThreads;
     // chunks: eighths of a wave (2368 drones = 5.9 MB, the first lanes start after ~0.1 ms) until the first
@@ -1434,6 +1474,8 @@ int fly_streamed_batch(const ld_params* params, const double* genomes, int64_t m
     // the kernel can never be left waiting for a copy the host has not issued yet (tools that make launches
     // synchronous — profilers, CUDA_LAUNCH_BLOCKING — would otherwise stall it until kWaitLimitNs).
     LD_CUDA(cudaMemsetAsync(w.ctl, 0, 4 * sizeof(unsigned long long), w.copy));
+    if (init_state) // start rows are small (224 B per drone): all of them go first
+        LD_CUDA(cudaMemcpyAsync(w.init, init_state, (size_t)m * LD_STATE_LEN * sizeof(double), cudaMemcpyHostToDevice, w.copy));
     LD_CUDA(cudaEventRecord(w.armed, w.copy));
     LD_CUDA(cudaStreamWaitEvent(w.compute, w.armed, 0)); // the kernel only waits for the counters to be reset
     int k = 0;
@@ -1447,8 +1489,12 @@ int fly_streamed_batch(const ld_params* params, const double* genomes, int64_t m
         LD_CUDA(cudaMemcpyAsync(w.ctl, w.h_counts + k, sizeof(unsigned long long), cudaMemcpyHostToDevice, w.copy));
     }
     int rc = launch_fly(params, w.genomes, m, w.records, final_state ? w.state : nullptr, reinterpret_cast<int64_t*>(w.ctl + 1),
-                        nullptr, w.compute, false, w.ctl, reinterpret_cast<int*>(w.ctl + 2));
-    if (rc) return rc;
+                        nullptr, w.compute, false, w.ctl, init_state ? w.init : nullptr);
+    if (rc) { // do not return while copies from the caller's buffers are still queued
+        cudaStreamSynchronize(w.copy);
+        cudaStreamSynchronize(w.compute);
+        return rc;
+    }
     LD_CUDA(cudaMemcpyAsync(records, w.records, (size_t)m * sizeof(ld_record), cudaMemcpyDeviceToHost, w.compute));
     if (final_state)
         LD_CUDA(cudaMemcpyAsync(final_state, w.state, (size_t)m * LD_STATE_LEN * sizeof(double), cudaMemcpyDeviceToHost, w.compute));
@@ -1457,6 +1503,84 @@ int fly_streamed_batch(const ld_params* params, const double* genomes, int64_t m
     LD_CUDA(cudaStreamSynchronize(w.compute));
     if (*w.h_error) return fail(LD_ERR_CUDA, "episode kernel gave up waiting for its work queue");
     return LD_OK;
+}
+
+// grow-only device scratch of the secondary *_host entry points (per host thread): no allocation per call
+constexpr int kScratchSlots = 6;
+struct Scratch {
+    int device = -1;
+    void* buf[kScratchSlots] = {};
+    size_t cap[kScratchSlots] = {};
+};
+thread_local Scratch g_scratch;
+
+void scratch_release() {
+    for (int i = 0; i < kScratchSlots; ++i) {
+        if (g_scratch.buf[i]) cudaFree(g_scratch.buf[i]);
+        g_scratch.buf[i] = nullptr;
+        g_scratch.cap[i] = 0;
+    }
+    g_scratch.device = -1;
+}
+
+int scratch_get(int slot, size_t bytes, void** out) {
+    int dev = 0;
+    LD_CUDA(cudaGetDevice(&dev));
+    if (g_scratch.device != dev) {
+        scratch_release();
+        g_scratch.device = dev;
+    }
+    if (g_scratch.cap[slot] < bytes) {
+        if (g_scratch.buf[slot]) cudaFree(g_scratch.buf[slot]);
+        g_scratch.buf[slot] = nullptr;
+        g_scratch.cap[slot] = 0;
+        size_t want = bytes < 4096 ? 4096 : bytes + bytes / 4;
+        LD_CUDA(cudaMalloc(&g_scratch.buf[slot], want));
+        g_scratch.cap[slot] = want;
+    }
+    *out = g_scratch.buf[slot];
+    return LD_OK;
+}
+
+// ---- generic brain forward (evolve/brain.py:41-54 for ANY layer_spec) and the two activations ----------------
+// One thread per input row; same arithmetic as the episode kernel's mlp_mac (k-ordered fma chain that starts
+// with the k = 0 product and ends with `+ bias`, ReLU on the sign bit, sigmoid_fast), so a 15-10-10-4 brain gives
+// the episode kernel's thrust bit for bit.
+constexpr int kBrainMaxLayers = 8, kBrainMaxWidth = 64;
+struct BrainSpec {
+    int n_layers;
+    int size[kBrainMaxLayers + 1]; // size[0] = inputs
+};
+
+__global__ void __launch_bounds__(128)
+brain_forward_kernel(const __grid_constant__ BrainSpec spec, const double* __restrict__ weights, long long weights_stride,
+                     const double* __restrict__ inputs, long long n, double* __restrict__ outputs, double neg_beta) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x[kBrainMaxWidth], y[kBrainMaxWidth];
+    const double* w = weights + i * weights_stride;
+    for (int k = 0; k < spec.size[0]; ++k) x[k] = inputs[i * spec.size[0] + k];
+    for (int l = 0; l < spec.n_layers; ++l) {
+        const int n_in = spec.size[l], n_out = spec.size[l + 1];
+        const bool last = l == spec.n_layers - 1;
+        for (int j = 0; j < n_out; ++j) {
+            const double* row = w + (long long)j * (n_in + 1);
+            double acc = row[0] * x[0];
+            for (int k = 1; k < n_in; ++k) acc = fma(row[k], x[k], acc);
+            acc = acc + row[n_in];
+            y[j] = last ? sigmoid_fast(acc, neg_beta) : relu(acc);
+        }
+        for (int j = 0; j < n_out; ++j) x[j] = y[j];
+        w += (long long)n_out * (n_in + 1);
+    }
+    const int n_last = spec.size[spec.n_layers];
+    for (int j = 0; j < n_last; ++j) outputs[i * n_last + j] = x[j];
+}
+
+// kind 0: NeuralNetwork._relu (brain.py:26-30) `0.0 if x < a else b * x`; kind 1: sigmoid (brain.py:37-39), beta = a
+__global__ void activation_kernel(int kind, const double* __restrict__ x, long long n, double* __restrict__ out, double a, double b) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = kind == 0 ? (x[i] < a ? 0.0 : b * x[i]) : sigmoid_fast(x[i], -a);
 }
 
 } // namespace
@@ -1506,17 +1630,20 @@ int ld_fly_mlp_f64_trace_device(const ld_params* params, const double* genome, l
     rc = ensure_device();
     if (rc) return rc;
     int64_t* counter = nullptr;
-    LD_CUDA(cudaMalloc((void**)&counter, sizeof(int64_t)));
-    rc = launch_fly(params, genome, 1, record, nullptr, counter, trace, (cudaStream_t)stream);
-    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
-    cudaFree(counter);
+    rc = scratch_get(0, 2 * sizeof(int64_t), (void**)&counter);
     if (rc) return rc;
+    rc = launch_fly(params, genome, 1, record, nullptr, counter, trace, (cudaStream_t)stream);
+    if (rc) return rc;
+    int err = 0;
+    cudaError_t e = cudaMemcpyAsync(&err, counter + 1, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
     if (e != cudaSuccess) return fail(LD_ERR_CUDA, "trace kernel", e);
+    if (err) return fail(LD_ERR_CUDA, "episode kernel gave up waiting for its work queue");
     return LD_OK;
 }
 
-static int fly_mlp_host_impl(const ld_params* params, const double* genomes, int64_t n, ld_record* records, double* final_state,
-                             bool f32) {
+static int fly_mlp_host_impl(const ld_params* params, const double* genomes, const double* init_state, int64_t n, ld_record* records,
+                             double* final_state, bool f32) {
     int rc = check_params(params);
     if (rc) return rc;
     if (n < 0) return fail(LD_ERR_INVALID_ARG, "n < 0");
@@ -1526,9 +1653,10 @@ static int fly_mlp_host_impl(const ld_params* params, const double* genomes, int
     if (rc) return rc;
     if (!f32) {
         const int64_t batch = n < kHostBatchMax ? n : kHostBatchMax;
-        rc = sws_reserve((size_t)batch, final_state != nullptr);
+        rc = sws_reserve((size_t)batch, final_state != nullptr, init_state != nullptr);
         for (int64_t off = 0; off < n && rc == LD_OK; off += batch)
-            rc = fly_streamed_batch(params, genomes + off * LD_GENOME_LEN, (n - off < batch) ? (n - off) : batch, records + off,
+            rc = fly_streamed_batch(params, genomes + off * LD_GENOME_LEN, init_state ? init_state + off * LD_STATE_LEN : nullptr,
+                                    (n - off < batch) ? (n - off) : batch, records + off,
                                     final_state ? final_state + off * LD_STATE_LEN : nullptr);
         return rc;
     }
@@ -1551,7 +1679,7 @@ static int fly_mlp_host_impl(const ld_params* params, const double* genomes, int
         LD_CUDA(cudaMemcpyAsync(g_ws.genomes[b], genomes + off * LD_GENOME_LEN, (size_t)m * LD_GENOME_LEN * sizeof(double),
                                 cudaMemcpyHostToDevice, s));
         rc = launch_fly(params, (const double*)g_ws.genomes[b], m, (ld_record*)g_ws.records[b],
-                        final_state ? (double*)g_ws.state[b] : nullptr, g_ws.counters + b, nullptr, s, f32);
+                        final_state ? (double*)g_ws.state[b] : nullptr, g_ws.counters + 2 * b, nullptr, s, f32);
         if (rc) return rc;
         LD_CUDA(cudaMemcpyAsync(records + off, g_ws.records[b], (size_t)m * sizeof(ld_record), cudaMemcpyDeviceToHost, s));
         if (final_state)
@@ -1564,11 +1692,27 @@ static int fly_mlp_host_impl(const ld_params* params, const double* genomes, int
 }
 
 int ld_fly_mlp_f64_host(const ld_params* params, const double* genomes, int64_t n, ld_record* records, double* final_state) {
-    return fly_mlp_host_impl(params, genomes, n, records, final_state, false);
+    return fly_mlp_host_impl(params, genomes, nullptr, n, records, final_state, false);
+}
+
+int ld_fly_mlp_f64_from_host(const ld_params* params, const double* genomes, const double* init_state, int64_t n, ld_record* records,
+                             double* final_state) {
+    return fly_mlp_host_impl(params, genomes, init_state, n, records, final_state, false);
+}
+
+int ld_fly_mlp_f64_from_device(const ld_params* params, const double* genomes, const double* init_state, int64_t n, ld_record* records,
+                               double* final_state, int64_t* work_counter, void* stream) {
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (n < 0) return fail(LD_ERR_INVALID_ARG, "n < 0");
+    if (n > 0 && (!genomes || !records || !work_counter)) return fail(LD_ERR_INVALID_ARG, "NULL device buffer");
+    if ((reinterpret_cast<uintptr_t>(genomes) & 15u) || (reinterpret_cast<uintptr_t>(records) & 15u))
+        return fail(LD_ERR_INVALID_ARG, "genomes and records must be 16-byte aligned");
+    return launch_fly(params, genomes, n, records, final_state, work_counter, nullptr, (cudaStream_t)stream, false, nullptr, init_state);
 }
 
 int ld_fly_mlp_f32_host(const ld_params* params, const double* genomes, int64_t n, ld_record* records, double* final_state) {
-    return fly_mlp_host_impl(params, genomes, n, records, final_state, true);
+    return fly_mlp_host_impl(params, genomes, nullptr, n, records, final_state, true);
 }
 
 int ld_fly_mlp_f32_device(const ld_params* params, const double* genomes, int64_t n, ld_record* records,
@@ -1642,25 +1786,32 @@ int ld_fly_pid_f64_device(const ld_params* params, const ld_pid_params* pid, con
 
 int ld_fly_pid_f64_host(const ld_params* params, const ld_pid_params* pid, const double* pid_gains, int64_t n,
                         ld_record* records, double* final_state) {
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (!pid || pid->n_coins < 1 || pid->n_coins > LD_PID_MAX_COINS || pid->timesteps < 0)
+        return fail(LD_ERR_INVALID_ARG, "bad ld_pid_params");
     if (n < 0) return fail(LD_ERR_INVALID_ARG, "n < 0");
     if (n == 0) return LD_OK;
     if (!pid_gains || !records) return fail(LD_ERR_INVALID_ARG, "NULL host buffer");
+    rc = ensure_device();
+    if (rc) return rc;
+    // validated: now the (grow-only, reused) device workspace and the work stream
+    rc = sws_reserve(1, false);
+    if (rc) return rc;
     double *d_gains = nullptr, *d_state = nullptr;
     ld_record* d_rec = nullptr;
-    LD_CUDA(cudaMalloc((void**)&d_gains, (size_t)n * 18 * sizeof(double)));
-    LD_CUDA(cudaMalloc((void**)&d_rec, (size_t)n * sizeof(ld_record)));
-    if (final_state) LD_CUDA(cudaMalloc((void**)&d_state, (size_t)n * LD_STATE_LEN * sizeof(double)));
-    int rc = LD_OK;
-    cudaError_t e = cudaMemcpy(d_gains, pid_gains, (size_t)n * 18 * sizeof(double), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) rc = ld_fly_pid_f64_device(params, pid, d_gains, n, d_rec, d_state, nullptr);
-    if (e == cudaSuccess && rc == LD_OK) e = cudaMemcpy(records, d_rec, (size_t)n * sizeof(ld_record), cudaMemcpyDeviceToHost);
+    if ((rc = scratch_get(1, (size_t)n * LD_PID_GAINS * sizeof(double), (void**)&d_gains))) return rc;
+    if ((rc = scratch_get(2, (size_t)n * sizeof(ld_record), (void**)&d_rec))) return rc;
+    if (final_state && (rc = scratch_get(3, (size_t)n * LD_STATE_LEN * sizeof(double), (void**)&d_state))) return rc;
+    cudaStream_t s = g_sws.compute;
+    cudaError_t e = cudaMemcpyAsync(d_gains, pid_gains, (size_t)n * LD_PID_GAINS * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) rc = ld_fly_pid_f64_device(params, pid, d_gains, n, d_rec, d_state, s);
+    if (e == cudaSuccess && rc == LD_OK) e = cudaMemcpyAsync(records, d_rec, (size_t)n * sizeof(ld_record), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess && rc == LD_OK && final_state)
-        e = cudaMemcpy(final_state, d_state, (size_t)n * LD_STATE_LEN * sizeof(double), cudaMemcpyDeviceToHost);
-    cudaFree(d_gains);
-    cudaFree(d_rec);
-    if (d_state) cudaFree(d_state);
+        e = cudaMemcpyAsync(final_state, d_state, (size_t)n * LD_STATE_LEN * sizeof(double), cudaMemcpyDeviceToHost, s);
+    const cudaError_t e_sync = cudaStreamSynchronize(s); // also on failure: nothing may still read the caller's buffers
     if (rc) return rc;
-    if (e != cudaSuccess) return fail(LD_ERR_CUDA, "ld_fly_pid_f64_host", e);
+    if (e != cudaSuccess || e_sync != cudaSuccess) return fail(LD_ERR_CUDA, "ld_fly_pid_f64_host", e != cudaSuccess ? e : e_sync);
     return LD_OK;
 }
 
@@ -1712,37 +1863,101 @@ int ld_drone_step_host(const ld_params* params, int what, const double* genomes,
     if (!state || (what == 1 && !flags) || (what == 2 && (!genomes || !coin))) return fail(LD_ERR_INVALID_ARG, "NULL host buffer");
     rc = ensure_device();
     if (rc) return rc;
+    rc = sws_reserve(1, false);
+    if (rc) return rc;
     double *d_state = nullptr, *d_gen = nullptr, *d_coin = nullptr;
     int* d_flags = nullptr;
-    cudaError_t e = cudaMalloc((void**)&d_state, (size_t)n * LD_STATE_LEN * sizeof(double));
-    if (e == cudaSuccess) e = cudaMemcpy(d_state, state, (size_t)n * LD_STATE_LEN * sizeof(double), cudaMemcpyHostToDevice);
+    if ((rc = scratch_get(1, (size_t)n * LD_STATE_LEN * sizeof(double), (void**)&d_state))) return rc;
     if (what == 1) {
-        if (e == cudaSuccess) e = cudaMalloc((void**)&d_flags, (size_t)n * 2 * sizeof(int));
+        if ((rc = scratch_get(2, (size_t)n * 2 * sizeof(int), (void**)&d_flags))) return rc;
     } else {
-        if (e == cudaSuccess) e = cudaMalloc((void**)&d_gen, (size_t)n * LD_GENOME_LEN * sizeof(double));
-        if (e == cudaSuccess) e = cudaMemcpy(d_gen, genomes, (size_t)n * LD_GENOME_LEN * sizeof(double), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&d_coin, (size_t)n * 3 * sizeof(double));
-        if (e == cudaSuccess) e = cudaMemcpy(d_coin, coin, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice);
+        if ((rc = scratch_get(3, (size_t)n * LD_GENOME_LEN * sizeof(double), (void**)&d_gen))) return rc;
+        if ((rc = scratch_get(4, (size_t)n * 3 * sizeof(double), (void**)&d_coin))) return rc;
+    }
+    cudaStream_t s = g_sws.compute;
+    cudaError_t e = cudaMemcpyAsync(d_state, state, (size_t)n * LD_STATE_LEN * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (what == 2) {
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_gen, genomes, (size_t)n * LD_GENOME_LEN * sizeof(double), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_coin, coin, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, s);
     }
     if (e == cudaSuccess) {
         const unsigned blocks = (unsigned)((n + 127) / 128);
-        if (has_extras(params)) drone_step_kernel<true><<<blocks, 128>>>(*params, what, d_gen, d_state, d_coin, d_flags, n);
-        else drone_step_kernel<false><<<blocks, 128>>>(*params, what, d_gen, d_state, d_coin, d_flags, n);
+        if (has_extras(params)) drone_step_kernel<true><<<blocks, 128, 0, s>>>(*params, what, d_gen, d_state, d_coin, d_flags, n);
+        else drone_step_kernel<false><<<blocks, 128, 0, s>>>(*params, what, d_gen, d_state, d_coin, d_flags, n);
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpy(state, d_state, (size_t)n * LD_STATE_LEN * sizeof(double), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && what == 1) e = cudaMemcpy(flags, d_flags, (size_t)n * 2 * sizeof(int), cudaMemcpyDeviceToHost);
-    cudaFree(d_state);
-    if (d_flags) cudaFree(d_flags);
-    if (d_gen) cudaFree(d_gen);
-    if (d_coin) cudaFree(d_coin);
-    if (e != cudaSuccess) return fail(LD_ERR_CUDA, "ld_drone_step_host", e);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(state, d_state, (size_t)n * LD_STATE_LEN * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && what == 1) e = cudaMemcpyAsync(flags, d_flags, (size_t)n * 2 * sizeof(int), cudaMemcpyDeviceToHost, s);
+    const cudaError_t e_sync = cudaStreamSynchronize(s);
+    if (e != cudaSuccess || e_sync != cudaSuccess) return fail(LD_ERR_CUDA, "ld_drone_step_host", e != cudaSuccess ? e : e_sync);
+    return LD_OK;
+}
+
+int ld_brain_forward_host(const int32_t* layer_sizes, int32_t n_layers, const double* weights, int64_t weights_stride, const double* inputs,
+                          int64_t n, double* outputs, double sigmoid_beta) {
+    if (!layer_sizes || n_layers < 1 || n_layers > kBrainMaxLayers) return fail(LD_ERR_INVALID_ARG, "1..8 layers");
+    BrainSpec spec;
+    memset(&spec, 0, sizeof(spec));
+    spec.n_layers = n_layers;
+    int64_t total = 0;
+    for (int l = 0; l <= n_layers; ++l) {
+        if (layer_sizes[l] < 1 || layer_sizes[l] > kBrainMaxWidth) return fail(LD_ERR_INVALID_ARG, "layer widths must be 1..64");
+        spec.size[l] = layer_sizes[l];
+        if (l > 0) total += (int64_t)layer_sizes[l] * (layer_sizes[l - 1] + 1);
+    }
+    if (n < 0) return fail(LD_ERR_INVALID_ARG, "n < 0");
+    if (n == 0) return LD_OK;
+    if (!weights || !inputs || !outputs) return fail(LD_ERR_INVALID_ARG, "NULL host buffer");
+    if (weights_stride != 0 && weights_stride < total) return fail(LD_ERR_INVALID_ARG, "weights_stride shorter than one brain");
+    int rc = ensure_device();
+    if (rc) return rc;
+    if ((rc = sws_reserve(1, false))) return rc;
+    const int64_t n_brains = weights_stride == 0 ? 1 : n; // stride 0: one brain shared by every input row
+    const int n_in = spec.size[0], n_out = spec.size[n_layers];
+    double *d_w = nullptr, *d_x = nullptr, *d_y = nullptr;
+    if ((rc = scratch_get(1, (size_t)n_brains * (weights_stride ? weights_stride : total) * sizeof(double), (void**)&d_w))) return rc;
+    if ((rc = scratch_get(2, (size_t)n * n_in * sizeof(double), (void**)&d_x))) return rc;
+    if ((rc = scratch_get(3, (size_t)n * n_out * sizeof(double), (void**)&d_y))) return rc;
+    cudaStream_t s = g_sws.compute;
+    cudaError_t e = cudaMemcpyAsync(d_w, weights, (size_t)n_brains * (weights_stride ? weights_stride : total) * sizeof(double),
+                                    cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, inputs, (size_t)n * n_in * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        brain_forward_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(spec, d_w, weights_stride, d_x, n, d_y, -sigmoid_beta);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(outputs, d_y, (size_t)n * n_out * sizeof(double), cudaMemcpyDeviceToHost, s);
+    const cudaError_t e_sync = cudaStreamSynchronize(s);
+    if (e != cudaSuccess || e_sync != cudaSuccess) return fail(LD_ERR_CUDA, "ld_brain_forward_host", e != cudaSuccess ? e : e_sync);
+    return LD_OK;
+}
+
+int ld_activation_host(int kind, const double* x, int64_t n, double* out, double a, double b) {
+    if ((kind != 0 && kind != 1) || n < 0 || (n > 0 && (!x || !out))) return fail(LD_ERR_INVALID_ARG, "bad arguments");
+    if (n == 0) return LD_OK;
+    int rc = ensure_device();
+    if (rc) return rc;
+    if ((rc = sws_reserve(1, false))) return rc;
+    double *d_x = nullptr, *d_y = nullptr;
+    if ((rc = scratch_get(1, (size_t)n * sizeof(double), (void**)&d_x))) return rc;
+    if ((rc = scratch_get(2, (size_t)n * sizeof(double), (void**)&d_y))) return rc;
+    cudaStream_t s = g_sws.compute;
+    cudaError_t e = cudaMemcpyAsync(d_x, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        long long blocks = (n + 255) / 256;
+        activation_kernel<<<(unsigned)(blocks > 1184 ? 1184 : blocks), 256, 0, s>>>(kind, d_x, n, d_y, a, b);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_y, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s);
+    const cudaError_t e_sync = cudaStreamSynchronize(s);
+    if (e != cudaSuccess || e_sync != cudaSuccess) return fail(LD_ERR_CUDA, "ld_activation_host", e != cudaSuccess ? e : e_sync);
     return LD_OK;
 }
 
 void ld_release_workspace(void) {
     ws_release();
     sws_release();
+    scratch_release();
     int dev = 0;
     cudaMemPool_t pool;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);

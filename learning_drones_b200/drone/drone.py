@@ -54,14 +54,21 @@ class Drone:
         if visualize or n_servers:
             raise NotImplementedError("the B200 fitness path is headless (visualize=False, n_servers=0)")
         self.port = port
-        self._initial = dict(
-            pos=_col(P.initial_pos if initial_pos is None else initial_pos, 3),
-            vel=_col(P.initial_vel if initial_vel is None else initial_vel, 3),
-            angle=_col(P.initial_angle if initial_angle is None else initial_angle, 3),
-            angle_vel=_col(P.initial_angle_vel if initial_angle_vel is None else initial_angle_vel, 3),
-        )
         self.controller = NeuralNetwork(layer_spec={1: 10, 2: 10, 3: 4})
-        self.reset()
+        # reference drone/drone.py:55-76: the CONSTRUCTOR arguments set the state the first flight starts from
+        # (attributes and the six Sensors); reset() below always goes back to the module-level defaults
+        self.distance_to_coin = np.inf
+        self.reward = 0
+        self.coins = 0
+        self.flight_time = 0
+        self.crashed = False
+        self.position = _col(P.initial_pos if initial_pos is None else initial_pos, 3)
+        self.velocity = _col(P.initial_vel if initial_vel is None else initial_vel, 3)
+        self.angle = _col(P.initial_angle if initial_angle is None else initial_angle, 3)
+        self.angle_vel = _col(P.initial_angle_vel if initial_angle_vel is None else initial_angle_vel, 3)
+        self.thrust = _col(P.initial_thrust, 4)
+        self.sensors = [Sensor(delta_t, self.position[i, 0], self.velocity[i, 0]) for i in range(3)]
+        self.sensors += [Sensor(delta_t, self.angle[i, 0], self.angle_vel[i, 0]) for i in range(3)]
 
     # reference drone/drone.py:177-218 (always resets to the module-level initial state)
     def reset(self):
@@ -143,17 +150,26 @@ class Drone:
 
     # -- used by flight.fly -------------------------------------------------------------------
     def start_state(self):
-        """State an episode starts from: whatever the attributes currently hold, as in the
-        reference where fly() continues from the Drone's state (fresh after __init__/reset())."""
-        if self.flight_time == 0 and self.reward == 0 and self.coins == 0:
-            return self.position, self.velocity, self.angle, self.angle_vel, self.thrust
-        raise RuntimeError("fly() on a Drone that already flew: call drone.reset() first (evolve/evolution.py:91-92)")
+        """(state row, reward, coins, flight_time, crashed) an episode starts from: whatever the Drone holds, as
+        in the reference where fly() continues from the Drone's state and adds to its counters
+        (flight/__init__.py:35-45).  The integrator reads the Sensors (previous_pos / previous_vel / accelerations),
+        the physics and the brain read the attributes (drone/drone.py:83-86,131-148); both are in the row."""
+        s = self._state_row()
+        pos = np.array([x.previous_pos for x in self.sensors], dtype=np.float64)
+        vel = np.array([x.previous_vel for x in self.sensors], dtype=np.float64)
+        attr_pos, attr_vel = np.concatenate([s[0:3], s[6:9]]), np.concatenate([s[3:6], s[9:12]])
+        if not (np.array_equal(pos, attr_pos) and np.array_equal(vel, attr_vel)):
+            raise ValueError("Drone attributes and Sensor state disagree (position/velocity/angle were edited without "
+                             "the sensors): the episode kernel keeps ONE copy of the kinematic state")
+        return s, int(self.reward), int(self.coins), int(self.flight_time), bool(self.crashed)
 
-    def load_result(self, record, state_row):
-        self.reward = int(record["reward"])
-        self.coins = int(record["coins"])
-        self.flight_time = int(record["flight_time"])
-        self.crashed = bool(record["status"] & 1)
+    def load_result(self, record, state_row, before=(0, 0, 0, False)):
+        """`before`: (reward, coins, flight_time, crashed) the Drone held when the episode started — the reference
+        adds to them (`drone.reward +=`, `drone.coins += 1`, `drone.flight_time += 1`; `crashed` is only ever set)."""
+        self.reward = before[0] + int(record["reward"])
+        self.coins = before[1] + int(record["coins"])
+        self.flight_time = before[2] + int(record["flight_time"])
+        self.crashed = before[3] or bool(record["status"] & 1)
         self.distance_to_coin = float(record["distance_to_coin"])
         s = np.asarray(state_row, dtype=np.float64).reshape(STATE_LEN)
         self._load_state_row(s)

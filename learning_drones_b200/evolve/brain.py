@@ -2,10 +2,9 @@
 
 `weights` is the list of per-layer (n_out, n_in + 1) float64 arrays, bias in the LAST column,
 that the reference's GA operators and jsonpickle checkpoints manipulate.  During fly() the
-forward pass runs inside the CUDA episode kernel (csrc/ldrones.cu `mlp_mac`), and
-`translate_input_to_thrust` of a Drone-shaped brain runs one GPU step; `feed_forward` is a
-host-side inspection helper with the reference's semantics (any layer shapes) that
-fly()/fly_population() never call.
+forward pass runs inside the CUDA episode kernel (csrc/ldrones.cu `mlp_mac`); single calls of
+`feed_forward` / `translate_input_to_thrust` / `relu` / `sigmoid` run on the GPU too, for any
+layer_spec (`ld_brain_forward_host`, `ld_activation_host`) — nothing here computes on the CPU.
 """
 import numpy as np
 import numpy.random as npr
@@ -50,39 +49,53 @@ class NeuralNetwork:
             o += r * c
         self.weights = out
 
-    # -- host-side inspection (reference semantics) -------------------------------------------
+    # -- forward pass and activations: always on the GPU (libldrones.so), for ANY layer_spec ------------------
+    def _layer_sizes(self):
+        return [int(np.shape(self.weights[0])[1]) - 1] + [int(np.shape(w)[0]) for w in self.weights]
+
     def _relu(self, x, thresh=0, alpha=1.0):
-        return 0.0 if x < thresh else alpha * x
+        """brain.py:26-30 for one scalar."""
+        return float(self.relu(np.array([[float(x)]]), thresh=thresh, alpha=alpha)[0, 0])
 
-    def relu(self, x_vec, thresh=0, alpha=1.0):
-        return np.array([[self._relu(x, thresh=thresh, alpha=alpha) for x in np.squeeze(x_vec)]]).T
-
-    def sigmoid(self, x, beta=0.4):
-        return 1 / (np.exp(-beta * x) + 1)
-
-    def feed_forward(self, input_vec):
-        x = input_vec
-        for i in range(self.n_layers):
-            x = np.dot(self.weights[i], np.vstack((x, [[1]])))
-            assert x.shape[1] == 1
-            x = self.sigmoid(x) if i == self.n_layers - 1 else self.relu(x)
-        return x
-
-    def translate_input_to_thrust(self, drone_position, drone_velocity, drone_angle, drone_angle_velocity, coin_position):
-        """(4, 1) thrust for one state.  Brains of the Drone's shape run on the GPU with the episode
-        kernel's arithmetic (ld_drone_step_host); other layer shapes use the host helper above."""
-        if not self.is_gpu_shape():
-            return self.feed_forward(np.vstack((drone_position, drone_velocity, drone_angle, drone_angle_velocity, coin_position)))
+    def _activation(self, kind, x, a, b):
         import ctypes as C
 
         from .. import _lib
-        from .._abi import STATE_LEN, make_params
 
-        state = np.zeros((1, STATE_LEN))
-        for lo, v in ((0, drone_position), (3, drone_velocity), (6, drone_angle), (9, drone_angle_velocity)):
-            state[0, lo:lo + 3] = np.asarray(v, dtype=np.float64).ravel()
-        genome = self.genome()[None, :].copy()
-        coin = np.asarray(coin_position, dtype=np.float64).reshape(1, 3).copy()
-        p = make_params(timesteps=1)
-        _lib.check(_lib.load().ld_drone_step_host(C.byref(p), 2, genome.ctypes.data, state.ctypes.data, coin.ctypes.data, None, 1))
-        return state[0, 24:28].reshape(4, 1).copy()
+        v = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
+        out = np.empty_like(v)
+        _lib.check(_lib.load().ld_activation_host(kind, v.ctypes.data, v.size, out.ctypes.data, C.c_double(a), C.c_double(b)))
+        return out
+
+    def relu(self, x_vec, thresh=0, alpha=1.0):
+        """brain.py:32-35: (n, 1) column of `0.0 if x < thresh else alpha * x`."""
+        return self._activation(0, np.squeeze(x_vec), float(thresh), float(alpha)).reshape(-1, 1)
+
+    def sigmoid(self, x, beta=0.4):
+        """brain.py:37-39: 1 / (exp(-beta x) + 1), same shape as x."""
+        return self._activation(1, x, float(beta), 0.0).reshape(np.shape(x))
+
+    def feed_forward(self, input_vec):
+        """brain.py:41-54 for whatever layer_spec this network has: bias appended LAST, hidden ReLU, output
+        sigmoid.  Runs in libldrones.so (ld_brain_forward_host) with the episode kernel's arithmetic."""
+        import ctypes as C
+
+        from .. import _lib
+
+        sizes = self._layer_sizes()
+        x = np.ascontiguousarray(np.asarray(input_vec, dtype=np.float64).reshape(1, -1))
+        if x.shape[1] != sizes[0]:
+            raise ValueError(f"input of {x.shape[1]} values for a network with {sizes[0]} inputs")
+        for w, n_in, n_out in zip(self.weights, sizes[:-1], sizes[1:]):
+            if np.shape(w) != (n_out, n_in + 1):
+                raise ValueError(f"layer of shape {np.shape(w)} does not follow a layer with {n_in} outputs")
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(w, dtype=np.float64).reshape(-1) for w in self.weights]))
+        out = np.empty((1, sizes[-1]))
+        spec = (C.c_int32 * len(sizes))(*sizes)
+        _lib.check(_lib.load().ld_brain_forward_host(spec, len(sizes) - 1, flat.ctypes.data, 0, x.ctypes.data, 1, out.ctypes.data, 0.4))
+        return out.reshape(-1, 1)
+
+    def translate_input_to_thrust(self, drone_position, drone_velocity, drone_angle, drone_angle_velocity, coin_position):
+        """brain.py:56-76: (n_out, 1) thrust for one state — stacks the 15 inputs and feeds them forward (GPU)."""
+        return self.feed_forward(np.vstack([np.asarray(v, dtype=np.float64).reshape(3, 1) for v in
+                                            (drone_position, drone_velocity, drone_angle, drone_angle_velocity, coin_position)]))

@@ -25,27 +25,27 @@ def fly_population(drones, timesteps: int = 2500, delta_t: float = 0.01, visuali
     if not drones:
         return []
     starts = [d.start_state() for d in drones]
-    first = starts[0]
-    for s in starts[1:]:
-        if not all(np.array_equal(a, b) for a, b in zip(first, s)):
-            raise ValueError("all drones of one fly_population() call must start from the same state")
-    params = make_params(
-        timesteps=timesteps, reward_time=reward_time, punish_time=punish_time,
-        initial_pos=first[0], initial_vel=first[1], initial_angle=first[2], initial_angle_vel=first[3],
-        initial_thrust=first[4],
-    )
+    params = make_params(timesteps=timesteps, reward_time=reward_time, punish_time=punish_time)
     genomes = np.stack([d.controller.genome() for d in drones])
-    records, state = fly_population_host(genomes, params, want_state=True)
+    rows = np.stack([s[0] for s in starts])
+    # every Drone freshly reset (the evolution loop, evolve/evolution.py:91-92): the kernel's own initial state;
+    # otherwise each drone continues from the state it holds (constructor arguments, a previous flight)
+    default_row = np.zeros(rows.shape[1])
+    default_row[0:3], default_row[3:6] = np.ravel(params.init_pos), np.ravel(params.init_vel)
+    default_row[6:9], default_row[9:12] = np.ravel(params.init_angle), np.ravel(params.init_angle_vel)
+    default_row[24:28] = np.ravel(params.init_thrust)
+    custom = not all(np.array_equal(r[:18], default_row[:18]) and np.array_equal(r[24:], default_row[24:]) for r in rows)
+    records, state = fly_population_host(genomes, params, want_state=True, init_state=rows if custom else None)
     out = []
     for i, d in enumerate(drones):
         if records[i]["status"] & STATUS_NONFINITE:
             # reference: REWARD_COIN_DISTANCE(nan) -> int(nan) raises (drone/drone.py:14)
             raise ValueError("cannot convert float NaN to integer")
-        d.load_result(records[i], state[i])
+        d.load_result(records[i], state[i], before=starts[i][1:])
         if timesteps <= 0:
             # reference: `real_time` is unbound when the loop body never runs (flight/__init__.py:99)
             raise UnboundLocalError("cannot access local variable 'real_time' where it is not associated with a value")
-        out.append((d.reward, (d.flight_time - 1) * delta_t, i))
+        out.append((d.reward, (int(records[i]["flight_time"]) - 1) * delta_t, i))  # real_time = last loop index * delta_t
     return out
 
 

@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._abi import GENOME_LEN, RECORD_DTYPE, STATE_LEN, LdParams, LdPidParams, make_params, make_pid_params
+from ._abi import GENOME_LEN, RECORD_DTYPE, STATE_LEN, LdParams, LdPidParams, make_params, make_pid_params, paramset_to_pid_gains
 
 RECORD_WORDS = RECORD_DTYPE.itemsize // 8  # records travel as int64[n][4] on the torch side
 
@@ -28,11 +28,13 @@ def _entry(L, precision: str, where: str):
     return getattr(L, f"ld_fly_mlp_{precision}_{where}")
 
 
-def fly_population_host(genomes, params: LdParams = None, want_state: bool = False, out=None, precision: str = "f64", **kw):
+def fly_population_host(genomes, params: LdParams = None, want_state: bool = False, out=None, precision: str = "f64",
+                        init_state=None, **kw):
     """genomes: (n, 314) float64 array-like in HOST memory -> (records[n] structured, state|None).
 
     `out` may be a preallocated RECORD_DTYPE array (e.g. backed by pinned memory).
     precision="f32" selects the float32 fast mode (no parity claim, see include/ldrones.h).
+    init_state: optional (n, 28) per-drone start rows (ld_fly_mlp_f64_from_host) replacing params.init_*.
     """
     L = _lib.load()
     p = _params(params, kw)
@@ -44,6 +46,15 @@ def fly_population_host(genomes, params: LdParams = None, want_state: bool = Fal
     if rec.dtype != RECORD_DTYPE or rec.shape != (n,) or not rec.flags.c_contiguous:
         raise ValueError("`out` must be a contiguous RECORD_DTYPE array of length n")
     st = np.empty((n, STATE_LEN), dtype=np.float64) if want_state else None
+    if init_state is not None:
+        if precision != "f64":
+            raise ValueError("per-drone start states are an fp64 (parity mode) feature")
+        s0 = np.ascontiguousarray(init_state, dtype=np.float64)
+        if s0.shape != (n, STATE_LEN):
+            raise ValueError(f"init_state must have shape ({n}, {STATE_LEN}), got {s0.shape}")
+        _lib.check(L.ld_fly_mlp_f64_from_host(C.byref(p), g.ctypes.data, s0.ctypes.data, n, rec.ctypes.data,
+                                              st.ctypes.data if want_state else None))
+        return rec, st
     _lib.check(
         _entry(L, precision, "host")(C.byref(p), g.ctypes.data, n, rec.ctypes.data, st.ctypes.data if want_state else None)
     )
@@ -52,11 +63,12 @@ def fly_population_host(genomes, params: LdParams = None, want_state: bool = Fal
 
 # ---- device tensors (torch owns the memory) ---------------------------------------------------
 def fly_population_device(genomes, params: LdParams = None, want_state: bool = False, records=None, state=None,
-                          work_counter=None, precision: str = "f64", **kw):
+                          work_counter=None, precision: str = "f64", init_state=None, **kw):
     """genomes: CUDA float64 tensor (n, 314).  Asynchronous on torch's current stream.
 
     Returns (records int64[n][4], state float64[n][28] | None); decode with `records_to_numpy`
-    or the `record_*` views below.
+    or the `record_*` views below.  `work_counter`: int64[2] CUDA scratch (queue head, error flag); pass your
+    own to look at the flag with `check_work_counter` once the stream has been synchronised.
     """
     import torch
 
@@ -74,20 +86,38 @@ def fly_population_device(genomes, params: LdParams = None, want_state: bool = F
         if want_state and state is None:
             state = torch.empty((n, STATE_LEN), dtype=torch.float64, device=dev)
         if work_counter is None:
-            work_counter = torch.empty(1, dtype=torch.int64, device=dev)
+            work_counter = torch.empty(2, dtype=torch.int64, device=dev)
+        if work_counter.numel() < 2 or work_counter.dtype != torch.int64 or not work_counter.is_cuda:
+            raise ValueError("work_counter must be a CUDA int64 tensor with 2 elements (queue head, error flag)")
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(
-            _entry(L, precision, "device")(
-                C.byref(p),
-                genomes.data_ptr(),
-                n,
-                records.data_ptr(),
-                state.data_ptr() if want_state else None,
-                work_counter.data_ptr(),
-                stream,
+        if init_state is not None:
+            if precision != "f64":
+                raise ValueError("per-drone start states are an fp64 (parity mode) feature")
+            if not (init_state.is_cuda and init_state.dtype == torch.float64 and init_state.is_contiguous()
+                    and tuple(init_state.shape) == (n, STATE_LEN)):
+                raise ValueError(f"init_state must be a contiguous CUDA float64 tensor of shape ({n}, {STATE_LEN})")
+            _lib.check(L.ld_fly_mlp_f64_from_device(C.byref(p), genomes.data_ptr(), init_state.data_ptr(), n, records.data_ptr(),
+                                                    state.data_ptr() if want_state else None, work_counter.data_ptr(), stream))
+        else:
+            _lib.check(
+                _entry(L, precision, "device")(
+                    C.byref(p),
+                    genomes.data_ptr(),
+                    n,
+                    records.data_ptr(),
+                    state.data_ptr() if want_state else None,
+                    work_counter.data_ptr(),
+                    stream,
+                )
             )
-        )
     return records, (state if want_state else None)
+
+
+def check_work_counter(work_counter):
+    """After the launch has completed: raise if the episode kernel gave up waiting for its work queue
+    (work_counter[1], see include/ldrones.h).  Synchronises."""
+    if int(work_counter[1].item()) != 0:
+        raise _lib.LdError(-2, "episode kernel gave up waiting for its work queue; records are incomplete")
 
 
 def records_to_numpy(records) -> np.ndarray:
@@ -150,12 +180,26 @@ def trace_drone(genome, params: LdParams = None, **kw):
 
 
 # ---- PID controller mode (flight/collect_coins.py as a batch over gain sets) ---------------------
-def fly_pid_population_host(pid_gains, params: LdParams = None, pid: LdPidParams = None, want_state: bool = False):
-    """pid_gains: (n, 6, 3) per-controller (kp, ki, kd) — see _abi.paramset_to_pid_gains — in HOST memory.
+def paramset_gains(paramset) -> np.ndarray:
+    """Gain set(s) of the reference's table by name — "11" or ["00", "11", ...] (drone/quadcopter/choose_paramset.py,
+    `run_simulation_without_viz.sh 11`) -> (n, 6, 3) per-controller (kp, ki, kd) wired like collect_coins.py:125-188."""
+    from .drone.quadcopter.choose_paramset import convert_paramset_2_float, get_paramset
+
+    names = [paramset] if isinstance(paramset, (str, int)) else list(paramset)
+    return paramset_to_pid_gains(np.array([convert_paramset_2_float(get_paramset(str(n))) for n in names], dtype=np.float64))
+
+
+def fly_pid_population_host(pid_gains=None, params: LdParams = None, pid: LdPidParams = None, want_state: bool = False, paramset=None):
+    """pid_gains: (n, 6, 3) per-controller (kp, ki, kd) — see _abi.paramset_to_pid_gains — in HOST memory, or
+    `paramset="11"` / a list of names from the reference's gain table (config 1 = paramset "11").
     Returns (records[n], state|None); records['reward'] is the script's final score."""
     L = _lib.load()
     p = make_params() if params is None else params
     q = make_pid_params() if pid is None else pid
+    if (pid_gains is None) == (paramset is None):
+        raise TypeError("pass either pid_gains or paramset")
+    if paramset is not None:
+        pid_gains = paramset_gains(paramset)
     g = np.ascontiguousarray(pid_gains, dtype=np.float64)
     if g.ndim != 3 or g.shape[1:] != (6, 3):
         raise ValueError(f"pid_gains must have shape (n, 6, 3), got {g.shape}")

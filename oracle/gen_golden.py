@@ -397,6 +397,76 @@ def main_large(out_dir, pool, n=8192):
     print("large fixture:", n, "drones; crashed", int(r["crashed"].sum()), "coins", int(r["coins"].sum()))
 
 
+def main_brain(out_dir):
+    """Reference NeuralNetwork (evolve/brain.py:10-76) for several layer_specs incl. its own default {1: 8, 2: 10, 3: 4}:
+    weights from np.random.seed, feed_forward / relu / sigmoid outputs."""
+    _import_reference()
+    with contextlib.redirect_stdout(io.StringIO()):
+        from evolve.brain import NeuralNetwork
+    out = {}
+    specs = {"default": (None, 15), "drone": ({1: 10, 2: 10, 3: 4}, 15), "small": ({1: 5, 2: 3}, 6), "deep": ({1: 12, 2: 7, 3: 9, 4: 2}, 20)}
+    for name, (spec, n_in) in specs.items():
+        np.random.seed(len(name))
+        nn = NeuralNetwork(n_inputs=n_in) if spec is None else NeuralNetwork(layer_spec=dict(spec), n_inputs=n_in)
+        xs = np.random.standard_normal((16, n_in, 1)) * np.random.uniform(0.1, 20.0, size=(16, 1, 1))
+        ys = np.array([nn.feed_forward(x) for x in xs])
+        out[f"{name}_sizes"] = np.array([n_in] + [w.shape[0] for w in nn.weights], dtype=np.int32)
+        out[f"{name}_weights"] = np.concatenate([w.flatten() for w in nn.weights])
+        out[f"{name}_inputs"], out[f"{name}_outputs"] = xs, ys
+    nn = NeuralNetwork()
+    v = np.linspace(-30.0, 30.0, 41).reshape(-1, 1)
+    out["act_x"], out["act_relu"], out["act_relu_t"], out["act_sigmoid"] = v, nn.relu(v), nn.relu(v, thresh=2.5, alpha=0.5), nn.sigmoid(v)
+    # thrust for a full state (brain.py:56-76)
+    np.random.seed(3)
+    nn = NeuralNetwork(layer_spec={1: 10, 2: 10, 3: 4})
+    args = [np.random.standard_normal((3, 1)) * s for s in (10, 3, 1, 5, 10)]
+    out["thrust_weights"] = np.concatenate([w.flatten() for w in nn.weights])
+    out["thrust_args"], out["thrust_out"] = np.array(args), nn.translate_input_to_thrust(*args)
+    np.savez_compressed(os.path.join(out_dir, "brain_forward.npz"), **out)
+    print("brain fixture:", {k: v.shape for k, v in out.items() if k.endswith("_outputs")})
+
+
+def main_starts(out_dir):
+    """fly() on Drones that are NOT in the reset state (flight/__init__.py:35-45 continues from whatever the Drone
+    holds): constructor arguments (drone/drone.py:20-76), and a second flight without reset()."""
+    Drone, fly = _import_reference()
+    rng = np.random.default_rng(99)
+    genomes = np.concatenate([survivors(6, rng), random_brains(10, rng)])
+    n = len(genomes)
+    init = dict(pos=rng.uniform(-3, 3, size=(n, 3)) + [0, 0, 20], vel=rng.uniform(-1, 1, size=(n, 3)),
+                angle=rng.uniform(-0.2, 0.2, size=(n, 3)), angle_vel=rng.uniform(-0.5, 0.5, size=(n, 3)))
+    first, second = [], []
+    for i, g in enumerate(genomes):
+        with contextlib.redirect_stdout(io.StringIO()):
+            d = Drone(visualize=False, n_servers=0, initial_pos=init["pos"][i].reshape(3, 1).copy(), initial_vel=init["vel"][i].reshape(3, 1).copy(),
+                      initial_angle=init["angle"][i].reshape(3, 1).copy(), initial_angle_vel=init["angle_vel"][i].reshape(3, 1).copy())
+        d.controller.weights = split_genome(g)
+        r1 = fly(d, timesteps=300, idx=i)
+        first.append((r1[0], r1[1], d.coins, d.flight_time, d.crashed, d.distance_to_coin, _state_row(d)))
+        r2 = fly(d, timesteps=200, idx=i)  # no reset: continues, counters accumulate, the coin schedule restarts
+        second.append((r2[0], r2[1], d.coins, d.flight_time, d.crashed, d.distance_to_coin, _state_row(d)))
+    pack = lambda rows, k: np.array([r[k] for r in rows])
+    out = dict(genomes=genomes, **{f"init_{k}": v for k, v in init.items()})
+    for name, rows in (("first", first), ("second", second)):
+        out.update({f"{name}_reward": pack(rows, 0).astype(np.int64), f"{name}_real_time": pack(rows, 1), f"{name}_coins": pack(rows, 2),
+                    f"{name}_flight_time": pack(rows, 3), f"{name}_crashed": pack(rows, 4), f"{name}_distance": pack(rows, 5),
+                    f"{name}_state": pack(rows, 6)})
+    np.savez_compressed(os.path.join(out_dir, "start_states.npz"), **out)
+    print("start-state fixture: first", out["first_reward"].tolist(), "second", out["second_reward"].tolist())
+
+
+if __name__ == "__main__" and "--starts-only" in sys.argv:
+    os.chdir(tempfile.mkdtemp(prefix="ld_golden_"))
+    main_starts(os.path.join(ROOT, "tests", "golden"))
+    sys.exit(0)
+
+
+if __name__ == "__main__" and "--brain-only" in sys.argv:
+    os.chdir(tempfile.mkdtemp(prefix="ld_golden_"))
+    main_brain(os.path.join(ROOT, "tests", "golden"))
+    sys.exit(0)
+
+
 if __name__ == "__main__" and "--evolution-only" in sys.argv:
     sys.argv.remove("--evolution-only")
     os.chdir(tempfile.mkdtemp(prefix="ld_golden_"))

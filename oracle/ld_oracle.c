@@ -227,9 +227,20 @@ static void finish(const ld_params* p, od_drone* d, int use_fma) {
     d->distance = dist;
 }
 
-/* flight/__init__.py:12-99 */
-static void fly(const ld_params* p, const double* g, od_drone* d, double* trace, int use_fma) {
+/* flight/__init__.py:12-99.  `start` (may be NULL): a state row the Drone holds when fly() is entered — constructor
+ * arguments (drone/drone.py:55-76) or what a previous flight left (the reference never resets inside fly(), :35-39);
+ * its counters are added by the caller (integer addition). */
+static void fly(const ld_params* p, const double* g, od_drone* d, double* trace, int use_fma, const double* start) {
     drone_reset(p, d);
+    if (start) {
+        memcpy(d->pos, start + 0, 24);
+        memcpy(d->vel, start + 3, 24);
+        memcpy(d->ang, start + 6, 24);
+        memcpy(d->rate, start + 9, 24);
+        memcpy(d->a_cur, start + 12, 48);
+        memcpy(d->a_last, start + 18, 48);
+        memcpy(d->thrust, start + 24, 32);
+    }
     for (int t = 0; t < p->timesteps; ++t) {
         if (p->punish_time) d->reward -= p->reward_time_passed; /* :41-42 */
         if (p->reward_time) d->reward += p->reward_time_passed; /* :43-44 */
@@ -273,6 +284,7 @@ typedef struct {
     double* final_state;
     int use_fma;
     atomic_llong* next;
+    const double* init_state;
 } od_job;
 
 #define OD_CHUNK 16
@@ -285,7 +297,7 @@ static void* od_worker(void* arg) {
         int64_t hi = lo + OD_CHUNK < j->n ? lo + OD_CHUNK : j->n;
         for (int64_t i = lo; i < hi; ++i) {
             od_drone d;
-            fly(j->p, j->genomes + i * LD_GENOME_LEN, &d, NULL, j->use_fma);
+            fly(j->p, j->genomes + i * LD_GENOME_LEN, &d, NULL, j->use_fma, j->init_state ? j->init_state + i * LD_STATE_LEN : NULL);
             emit(&d, j->records + i, j->final_state ? j->final_state + i * LD_STATE_LEN : NULL);
         }
     }
@@ -299,13 +311,21 @@ int ld_oracle_max_threads(void) {
 
 /* population loop of evolve/evolution.py:64-73, fanned out over `nthreads` host threads
  * (<=0: all online cores); drones are independent so the result does not depend on it */
+int ld_oracle_fly_mlp_from(const ld_params* p, const double* genomes, const double* init_state, int64_t n, ld_record* records,
+                           double* final_state, int use_fma, int nthreads);
+
 int ld_oracle_fly_mlp(const ld_params* p, const double* genomes, int64_t n, ld_record* records,
                       double* final_state, int use_fma, int nthreads) {
+    return ld_oracle_fly_mlp_from(p, genomes, NULL, n, records, final_state, use_fma, nthreads);
+}
+
+int ld_oracle_fly_mlp_from(const ld_params* p, const double* genomes, const double* init_state, int64_t n, ld_record* records,
+                           double* final_state, int use_fma, int nthreads) {
     if (!p || !genomes || !records || n < 0) return LD_ERR_INVALID_ARG;
     if (nthreads <= 0) nthreads = ld_oracle_max_threads();
     if (nthreads > 256) nthreads = 256;
     atomic_llong next = 0;
-    od_job job = {p, genomes, n, records, final_state, use_fma, &next};
+    od_job job = {p, genomes, n, records, final_state, use_fma, &next, init_state};
     pthread_t tid[256];
     int started = 0;
     for (int t = 1; t < nthreads; ++t)
@@ -318,7 +338,7 @@ int ld_oracle_fly_mlp(const ld_params* p, const double* genomes, int64_t n, ld_r
 int ld_oracle_trace_mlp(const ld_params* p, const double* genome, ld_record* record, double* trace, int use_fma) {
     if (!p || !genome || !record || !trace) return LD_ERR_INVALID_ARG;
     od_drone d;
-    fly(p, genome, &d, trace, use_fma);
+    fly(p, genome, &d, trace, use_fma, NULL);
     emit(&d, record, NULL);
     return LD_OK;
 }

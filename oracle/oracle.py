@@ -38,6 +38,8 @@ def lib():
         dp = C.POINTER(C.c_double)
         L.ld_oracle_fly_mlp.argtypes = [C.POINTER(LdParams), dp, C.c_int64, C.POINTER(LdRecord), dp, C.c_int, C.c_int]
         L.ld_oracle_fly_mlp.restype = C.c_int
+        L.ld_oracle_fly_mlp_from.argtypes = [C.POINTER(LdParams), dp, dp, C.c_int64, C.POINTER(LdRecord), dp, C.c_int, C.c_int]
+        L.ld_oracle_fly_mlp_from.restype = C.c_int
         L.ld_oracle_trace_mlp.argtypes = [C.POINTER(LdParams), dp, C.POINTER(LdRecord), dp, C.c_int]
         L.ld_oracle_trace_mlp.restype = C.c_int
         L.ld_oracle_accelerations.argtypes = [C.POINTER(LdParams), dp, dp, dp, dp, C.c_int]
@@ -60,15 +62,18 @@ def max_threads() -> int:
     return int(lib().ld_oracle_max_threads())
 
 
-def fly_mlp(params: LdParams, genomes, use_fma: bool = True, nthreads: int = 0, want_state: bool = False):
-    """Population loop around the reference's fly() — returns (records, final_state|None)."""
+def fly_mlp(params: LdParams, genomes, use_fma: bool = True, nthreads: int = 0, want_state: bool = False, init_state=None):
+    """Population loop around the reference's fly() — returns (records, final_state|None).
+    init_state: optional (n, 28) rows the Drones hold when fly() is entered (counters of the episode start at 0)."""
     g = np.ascontiguousarray(genomes, dtype=np.float64).reshape(-1, GENOME_LEN)
     n = g.shape[0]
     rec = np.zeros(n, dtype=RECORD_DTYPE)
     st = np.zeros((n, STATE_LEN), dtype=np.float64) if want_state else None
-    rc = lib().ld_oracle_fly_mlp(
+    s0 = None if init_state is None else np.ascontiguousarray(init_state, dtype=np.float64).reshape(n, STATE_LEN)
+    rc = lib().ld_oracle_fly_mlp_from(
         C.byref(params),
         _dptr(g),
+        _dptr(s0) if s0 is not None else None,
         n,
         rec.ctypes.data_as(C.POINTER(LdRecord)),
         _dptr(st) if want_state else None,

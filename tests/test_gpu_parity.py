@@ -448,13 +448,88 @@ def test_stepping_a_drone_by_hand_equals_fly(golden):
     np.testing.assert_allclose(a.position.ravel(), g["state"][0, :3], rtol=1e-7)
 
 
-def test_brain_single_call_matches_host_helper():
+def test_brain_forward_matches_reference_fixture(golden):
+    """NeuralNetwork.feed_forward / translate_input_to_thrust / relu / sigmoid run in libldrones.so for ANY layer_spec
+    (no host fallback); fixture = the reference's own NeuralNetwork incl. its default {1: 8, 2: 10, 3: 4}.
+    Tolerance 1e-13 relative: the reference's np.dot is an OpenBLAS dgemv whose summation order is host specific."""
     from learning_drones_b200.evolve.brain import NeuralNetwork
 
-    np.random.seed(9)
-    nn = NeuralNetwork(layer_spec={1: 10, 2: 10, 3: 4})
-    args = [np.random.standard_normal((3, 1)) * s for s in (10, 3, 1, 5, 10)]
-    gpu = nn.translate_input_to_thrust(*args)
-    host = nn.feed_forward(np.vstack(args))
-    assert gpu.shape == (4, 1)
-    np.testing.assert_allclose(gpu, host, rtol=1e-12, atol=1e-15)
+    g = golden("brain_forward")
+    for name in ("default", "drone", "small", "deep"):
+        sizes = g[f"{name}_sizes"].tolist()
+        spec = {i + 1: s for i, s in enumerate(sizes[1:])}
+        nn = NeuralNetwork(n_inputs=sizes[0]) if name == "default" else NeuralNetwork(layer_spec=spec, n_inputs=sizes[0])
+        assert [w.shape for w in nn.weights] == [(o, i + 1) for i, o in zip(sizes[:-1], sizes[1:])]
+        o, ws = 0, []
+        for i, n_out in zip(sizes[:-1], sizes[1:]):
+            ws.append(g[f"{name}_weights"][o:o + n_out * (i + 1)].reshape(n_out, i + 1).copy())
+            o += n_out * (i + 1)
+        nn.weights = ws
+        for x, y in zip(g[f"{name}_inputs"], g[f"{name}_outputs"]):
+            got = nn.feed_forward(x)
+            assert got.shape == y.shape
+            np.testing.assert_allclose(got, y, rtol=1e-13, atol=1e-300)
+    nn = NeuralNetwork()
+    assert np.array_equal(nn.relu(g["act_x"]), g["act_relu"]) and np.array_equal(nn.relu(g["act_x"], thresh=2.5, alpha=0.5), g["act_relu_t"])
+    np.testing.assert_allclose(nn.sigmoid(g["act_x"]), g["act_sigmoid"], rtol=4e-16 * 4)
+    assert nn._relu(-1.0) == 0.0 and nn._relu(3.0) == 3.0
+    drone_nn = NeuralNetwork(layer_spec={1: 10, 2: 10, 3: 4})
+    drone_nn.set_genome(g["thrust_weights"])
+    thrust = drone_nn.translate_input_to_thrust(*g["thrust_args"])
+    np.testing.assert_allclose(thrust, g["thrust_out"], rtol=1e-13)
+    with pytest.raises(ValueError):
+        drone_nn.feed_forward(np.zeros((7, 1)))
+
+
+def test_fly_continues_from_drone_state(pop, oracle, golden):
+    """Drone(initial_pos=...) flies from its constructor arguments, and fly() on a Drone that already flew continues
+    from its state and adds to its counters — like the reference (fixture: oracle/gen_golden.py --starts-only)."""
+    from learning_drones_b200.drone.drone import Drone
+    from learning_drones_b200.flight import fly, fly_population
+
+    g = golden("start_states")
+    n = len(g["genomes"])
+    col = lambda a: np.asarray(a, dtype=np.float64).reshape(3, 1)
+    drones = []
+    for i in range(n):
+        d = Drone(visualize=False, n_servers=0, initial_pos=col(g["init_pos"][i]), initial_vel=col(g["init_vel"][i]),
+                  initial_angle=col(g["init_angle"][i]), initial_angle_vel=col(g["init_angle_vel"][i]))
+        d.controller.set_genome(g["genomes"][i])
+        assert np.array_equal(d.position, col(g["init_pos"][i])) and d.sensors[3].previous_pos == g["init_angle"][i][0]
+        drones.append(d)
+    out = fly_population(drones, timesteps=300)
+    assert [o[0] for o in out] == g["first_reward"].tolist() == [d.reward for d in drones]
+    assert [d.flight_time for d in drones] == g["first_flight_time"].tolist() and [d.crashed for d in drones] == g["first_crashed"].tolist()
+    np.testing.assert_allclose([o[1] for o in out], g["first_real_time"], atol=1e-12)
+    np.testing.assert_allclose(np.array([d._state_row() for d in drones]), g["first_state"], rtol=1e-7, atol=1e-8)
+    # second flight WITHOUT reset: half through fly() one by one, half as a population
+    second = [fly(d, timesteps=200, idx=i) for i, d in enumerate(drones[: n // 2])]
+    second += [(r, t, n // 2 + i) for i, (r, t, _) in enumerate(fly_population(drones[n // 2:], timesteps=200))]
+    assert [o[0] for o in second] == g["second_reward"].tolist() == [d.reward for d in drones]
+    assert [d.flight_time for d in drones] == g["second_flight_time"].tolist() and [d.coins for d in drones] == g["second_coins"].tolist()
+    assert [d.crashed for d in drones] == g["second_crashed"].tolist()
+    np.testing.assert_allclose([o[1] for o in second], g["second_real_time"], atol=1e-12)
+    np.testing.assert_allclose([d.distance_to_coin for d in drones], g["second_distance"], rtol=1e-6)
+    # reset() goes back to the module-level initial state whatever the constructor was given (drone.py:177-218)
+    drones[0].reset()
+    assert drones[0].position.ravel().tolist() == [0.0, 0.0, 10.0] and drones[0].reward == 0
+    # device entry point with per-drone start rows == oracle, mixed population larger than one wave of lanes
+    import torch
+
+    rng = np.random.default_rng(5)
+    m = 20000
+    genomes = np.concatenate([g["genomes"]] * (m // n + 1))[:m]
+    rows = np.zeros((m, STATE_LEN))
+    rows[:, 0:3] = rng.uniform(-3, 3, size=(m, 3)) + [0, 0, 20]
+    rows[:, 3:12] = rng.uniform(-0.3, 0.3, size=(m, 9))
+    rows[:, 12:18] = rng.uniform(-1, 1, size=(m, 6))
+    rows[:, 24:28] = rng.uniform(0, 0.4, size=(m, 4))
+    p = make_params(400)
+    p.slice_steps = 100
+    ref, rst = oracle.fly_mlp(p, genomes, want_state=True, init_state=rows)
+    rec_t, st_t = pop.fly_population_device(torch.from_numpy(genomes).cuda(), p, want_state=True, init_state=torch.from_numpy(rows).cuda())
+    rec = pop.records_to_numpy(rec_t)
+    same = (rec["reward"] == ref["reward"]) & (rec["flight_time"] == ref["flight_time"])
+    assert same.mean() > 0.995, same.mean()
+    rec_h, _ = pop.fly_population_host(genomes, p, init_state=rows)
+    assert rec_h.tobytes() == rec.tobytes()

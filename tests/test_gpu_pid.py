@@ -56,3 +56,18 @@ def test_pid_kernel_matches_oracle_batch(oracle, golden):
     # ragged / empty
     assert pop.fly_pid_population_host(pg[:0], p, q)[0].shape == (0,)
     assert pop.fly_pid_population_host(pg[:33], p, q)[0].tobytes() == rec[:33].tobytes()
+
+
+def test_config1_by_paramset_name():
+    """BASELINE.json configs[0]: `run_simulation_without_viz.sh 11` — the headless coin-collection flight with the
+    reference's gain set "11", named through the API (no fixture involved): Final Score 5923 after 1577 steps."""
+    from learning_drones_b200 import population as pop
+
+    rec, _ = pop.fly_pid_population_host(paramset="11")
+    assert (int(rec["reward"][0]), int(rec["flight_time"][0]), int(rec["coins"][0])) == (5923, 1577, 4)
+    assert rec["status"][0] & STATUS_FINISHED
+    names = ["00", "01", "02", "10", "11", "12", "13", "20", "21", "22"]
+    rec, _ = pop.fly_pid_population_host(paramset=names)  # compare_paramsets.sh: nine GUI runs -> one launch
+    assert rec["reward"].tolist() == [6059, 5860, 5198, 5933, 5923, 5990, 5946, 6098, 5910, 5928]
+    with pytest.raises(TypeError):
+        pop.fly_pid_population_host()

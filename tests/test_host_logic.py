@@ -94,11 +94,22 @@ def test_drone_reset_and_guards():
     d = Drone(visualize=False, n_servers=0)
     assert d.position.shape == (3, 1) and d.thrust.shape == (4, 1) and d.distance_to_coin == np.inf
     assert len(d.sensors) == 6 and d.sensors[2].previous_pos == 10.0
+    # constructor arguments set the state the first flight starts from (reference drone/drone.py:55-76) ...
+    e = Drone(initial_pos=np.array([[1.0], [2.0], [30.0]]), initial_angle_vel=np.array([[0.1], [0.2], [0.3]]))
+    assert e.position.ravel().tolist() == [1.0, 2.0, 30.0] and e.sensors[5].previous_vel == 0.3 and e.sensors[1].previous_pos == 2.0
+    row, reward, coins, flight_time, crashed = e.start_state()
+    assert row[:3].tolist() == [1.0, 2.0, 30.0] and row[9:12].tolist() == [0.1, 0.2, 0.3] and (reward, coins, flight_time, crashed) == (0, 0, 0, False)
+    # ... a Drone that already flew continues from what it holds (flight/__init__.py:35-45) ...
     d.reward, d.flight_time = 5, 3
-    with pytest.raises(RuntimeError):
+    assert d.start_state()[1:] == (5, 0, 3, False)
+    d.position = d.position + 1.0  # attributes edited behind the sensors' back: refused, not silently flown
+    with pytest.raises(ValueError):
         d.start_state()
+    # ... and reset() always goes back to the module-level initial state (:177-218)
     d.reset()
+    e.reset()
     assert d.reward == 0 and d.flight_time == 0 and not d.crashed
+    assert e.position.ravel().tolist() == [0.0, 0.0, 10.0] and e.sensors[5].previous_vel == 0.0
     with pytest.raises(NotImplementedError):
         Drone(visualize=True, n_servers=1)
 
@@ -131,8 +142,14 @@ def test_mirror_classes_match_reference_under_same_seed(tmp_path, monkeypatch):
     np.random.seed(11)
     b = NeuralNetwork(layer_spec={1: 10, 2: 10, 3: 4})
     assert all(np.array_equal(x, y) for x, y in zip(a.weights, b.weights))
-    x = np.random.standard_normal((15, 1))
-    assert np.array_equal(a.feed_forward(x), b.feed_forward(x))
+    # the reference's own default layer_spec {1: 8, 2: 10, 3: 4} (evolve/brain.py:10)
+    np.random.seed(12)
+    a = rbrain.NeuralNetwork()
+    np.random.seed(12)
+    b = NeuralNetwork()
+    assert [w.shape for w in b.weights] == [(8, 16), (10, 9), (4, 11)] and b.n_layers == a.n_layers == 3
+    assert all(np.array_equal(x, y) for x, y in zip(a.weights, b.weights))
+    # (feed_forward itself runs on the GPU: tests/test_gpu_parity.py::test_brain_forward_matches_reference_fixture)
 
     def population(cls, seed, n=8):
         np.random.seed(seed)

@@ -126,3 +126,22 @@ def test_oracle_matches_reference_large(oracle, golden):
     # among ALL drones (chaotic ones included) only a handful may differ
     same = (rec["reward"] == g["reward"]) & (rec["flight_time"] == g["flight_time"])
     assert same.mean() > 0.995
+
+
+def test_oracle_continues_from_drone_state(oracle, golden):
+    """fly() on Drones that are not in the reset state (constructor arguments; a second flight without reset()):
+    the reference continues from the Drone's state and adds to its counters (flight/__init__.py:35-45)."""
+    g = golden("start_states")
+    n = len(g["genomes"])
+    rows = np.zeros((n, 28))
+    rows[:, 0:3], rows[:, 3:6], rows[:, 6:9], rows[:, 9:12] = g["init_pos"], g["init_vel"], g["init_angle"], g["init_angle_vel"]
+    r1, s1 = oracle.fly_mlp(make_params(300), g["genomes"], want_state=True, init_state=rows)
+    assert r1["reward"].tolist() == g["first_reward"].tolist() and r1["flight_time"].tolist() == g["first_flight_time"].tolist()
+    assert r1["coins"].tolist() == g["first_coins"].tolist()
+    np.testing.assert_allclose(s1, g["first_state"], rtol=1e-7, atol=1e-8)
+    r2, s2 = oracle.fly_mlp(make_params(200), g["genomes"], want_state=True, init_state=s1)
+    assert (r1["reward"] + r2["reward"]).tolist() == g["second_reward"].tolist()
+    assert (r1["flight_time"] + r2["flight_time"]).tolist() == g["second_flight_time"].tolist()
+    np.testing.assert_allclose((r2["flight_time"] - 1) * 0.01, g["second_real_time"], atol=1e-12)
+    ok = np.isfinite(g["second_state"]).all(axis=1)
+    np.testing.assert_allclose(s2[ok], g["second_state"][ok], rtol=1e-6, atol=1e-7)

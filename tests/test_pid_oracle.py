@@ -49,3 +49,21 @@ def test_pid_oracle_trajectory(oracle, golden):
     assert n == int(rec["flight_time"][0]) - 1  # the exit step breaks before the physics
     np.testing.assert_allclose(tr[:n], ref, rtol=1e-7, atol=1e-9)
     assert np.isnan(tr[n:]).all()
+
+
+def test_paramset_table_matches_reference_fixture(golden):
+    """drone/quadcopter/choose_paramset.py mirror: every named gain set equals what the reference's own get_paramset +
+    convert_paramset_2_float returned when the fixture was generated (oracle/gen_golden.py `pid_gains`)."""
+    from learning_drones_b200.drone.quadcopter import choose_paramset as cp
+    from learning_drones_b200.population import paramset_gains
+
+    g = golden("pid_collect_coins")
+    names = [str(n) for n in g["paramsets"]]
+    assert set(names) == set(cp.PARAMSET_NAMES) and len(names) == 10
+    for i, name in enumerate(names):
+        d = cp.get_paramset(name)
+        assert len(d) == 18 and np.array_equal(np.array(cp.convert_paramset_2_float(d)), g["gains"][i])
+    assert np.array_equal(paramset_gains(names), paramset_to_pid_gains(g["gains"][:10]))
+    assert paramset_gains("11").shape == (1, 6, 3) and paramset_gains("11")[0, 2, 1] == 0.1  # z PID uses ki_y (collect_coins.py:181)
+    with pytest.raises(Exception, match="Invalid Parameter Set"):
+        cp.get_paramset("default")
