@@ -21,6 +21,8 @@ import numpy as np
 REF = os.environ.get("LD_REFERENCE", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 LAYER_SHAPES = ((10, 16), (10, 11), (4, 11))
 GENOME_LEN = 314
@@ -458,6 +460,32 @@ def main_starts(out_dir):
 if __name__ == "__main__" and "--starts-only" in sys.argv:
     os.chdir(tempfile.mkdtemp(prefix="ld_golden_"))
     main_starts(os.path.join(ROOT, "tests", "golden"))
+    sys.exit(0)
+
+
+def main_checkpoint(out_dir):
+    """evolution/best_drone_<t>.json as the reference writes it (evolve/evolution.py:80-87): the seed-0 Drone after its
+    flight, deep-copied, jsonpickle-encoded (restated pickler, oracle/mini_jsonpickle.py — jsonpickle itself is not
+    installed here) and json.dump-ed a second time."""
+    import json
+    from copy import deepcopy
+
+    from oracle import mini_jsonpickle as mj
+
+    Drone, fly = _import_reference()
+    np.random.seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        d = Drone(visualize=False, n_servers=0)
+    fly(d, idx=0)
+    best = deepcopy(d)
+    with open(os.path.join(out_dir, "reference_best_drone.json"), "w") as f:
+        json.dump(mj.encode(best), f)
+    print("checkpoint fixture: reward", best.reward, "flight_time", best.flight_time)
+
+
+if __name__ == "__main__" and "--checkpoint-only" in sys.argv:
+    os.chdir(tempfile.mkdtemp(prefix="ld_golden_"))
+    main_checkpoint(os.path.join(ROOT, "tests", "golden"))
     sys.exit(0)
 
 

@@ -276,26 +276,84 @@ def test_properties_with_hypothesis():
 
 
 def test_best_drone_checkpoint_round_trip(tmp_path):
-    """persist the best drone (evolution.py:85-87) and load it back (fly_best_drone.py:11-14)."""
+    """persist the best drone (evolution.py:85-87) and load it back (fly_best_drone.py:11-14), in the
+    reference's double-encoded jsonpickle format (default) and in the plain one; no RNG draws while loading."""
+    import json
+
     from learning_drones_b200 import checkpoint
     from learning_drones_b200.drone.drone import Drone
 
     np.random.seed(5)
     d = Drone()
     d.reward, d.coins, d.flight_time, d.crashed, d.distance_to_coin = -4077, 3, 170, True, 1.0 / 3.0
-    path = checkpoint.save_drone(d, tmp_path / "best_drone.json")
-    e = checkpoint.load_drone(path)
-    assert all(np.array_equal(a, b) for a, b in zip(d.controller.weights, e.controller.weights))  # bit for bit
-    assert np.array_equal(d.controller.genome(), e.controller.genome())
-    assert (e.reward, e.coins, e.flight_time, e.crashed, e.distance_to_coin) == (-4077, 3, 170, True, 1.0 / 3.0)
-    assert e.controller.layer_spec == d.controller.layer_spec
+    for fmt in ("jsonpickle", "plain"):
+        path = checkpoint.save_drone(d, tmp_path / f"best_drone_{fmt}.json", fmt=fmt)
+        rng_before = np.random.get_state()[1].copy()
+        e = checkpoint.load_drone(path)
+        assert np.array_equal(np.random.get_state()[1], rng_before)  # loading does not consume numpy's global stream
+        assert all(np.array_equal(a, b) for a, b in zip(d.controller.weights, e.controller.weights))  # bit for bit
+        assert np.array_equal(d.controller.genome(), e.controller.genome())
+        assert (e.reward, e.coins, e.flight_time, e.crashed, e.distance_to_coin) == (-4077, 3, 170, True, 1.0 / 3.0)
+        assert e.controller.layer_spec == d.controller.layer_spec and e.controller.n_layers == 3
+    with open(tmp_path / "best_drone_jsonpickle.json") as f:
+        text = json.load(f)
+    assert isinstance(text, str)  # evolution.py:85-87 dumps the jsonpickle TEXT: a JSON string, not an object
+    doc = json.loads(text)
+    assert doc["py/object"] == "drone.drone.Drone" and doc["controller"]["py/object"] == "evolve.brain.NeuralNetwork"
+    assert list(doc)[1:] == ["quadcopter", "dh", "sensors", "controller", "distance_to_coin", "reward", "coins", "flight_time",
+                             "crashed", "position", "velocity", "angle", "angle_vel", "thrust"]  # Drone.__init__ order
+    assert doc["controller"]["layer_spec"] == {"1": 10, "2": 10, "3": 4, "0": 15}
+    d.distance_to_coin = np.inf  # a Drone that never flew (drone.py:67): json.dump writes Infinity like the reference's file
+    assert checkpoint.load_drone(checkpoint.save_drone(d, tmp_path / "inf.json")).distance_to_coin == np.inf
     with pytest.raises(ValueError):
         checkpoint.save_drone(d, tmp_path / "x.json", fmt="pickle")
-    try:
-        import jsonpickle  # noqa: F401
-    except ImportError:
-        with pytest.raises(ImportError):  # the reference's format is never emulated without its library
-            checkpoint.save_drone(d, tmp_path / "ref.json", fmt="jsonpickle")
-    else:
-        f = checkpoint.load_drone(checkpoint.save_drone(d, tmp_path / "ref.json", fmt="jsonpickle"))
-        assert all(np.array_equal(a, b) for a, b in zip(d.controller.weights, f.controller.weights))
+
+
+def test_reads_reference_checkpoint_fixture(golden):
+    """tests/golden/reference_best_drone.json = the reference's seed-0 Drone after its flight, encoded the way
+    jsonpickle encodes it (py/object tags, ndarray / numpy-scalar __reduce__ forms, py/id back-references to the shared
+    dtype; oracle/gen_golden.py --checkpoint-only)."""
+    from learning_drones_b200 import checkpoint
+
+    d = checkpoint.load_drone(os.path.join(ROOT, "tests", "golden", "reference_best_drone.json"))
+    g = golden("seed0_single")
+    assert np.array_equal(d.controller.genome(), g["genomes"][0])  # every weight bit for bit
+    assert (d.reward, d.flight_time, d.coins, d.crashed) == (-4077, 170, 0, True) and d.distance_to_coin == 11.208182019123052
+    assert d.controller.layer_spec == {1: 10, 2: 10, 3: 4, 0: 15}
+    assert d.position.ravel().tolist() == [0.0, 0.0, 10.0]  # in the reset state, like fly_best_drone.py:14 leaves it
+
+
+@needs_ref
+def test_our_checkpoint_replays_in_the_reference(tmp_path, monkeypatch):
+    """A file written by save_drone decodes into the REFERENCE's own Drone class (through the restated jsonpickle
+    unpickler, oracle/mini_jsonpickle.py) and re-flies there with the known result — fly_best_drone.py:11-20."""
+    import json
+
+    monkeypatch.chdir(tmp_path)
+    rdrone, rbrain, rutil = _ref_modules()
+    with contextlib.redirect_stdout(io.StringIO()):
+        from flight import fly as ref_fly
+        import drone.sensor.sensor as rsensor
+    from learning_drones_b200 import checkpoint
+    from learning_drones_b200.drone.drone import Drone
+    from oracle import mini_jsonpickle as mj
+
+    np.random.seed(0)
+    ours = Drone()
+    path = checkpoint.save_drone(ours, tmp_path / "best_drone_1.json")
+    with open(path) as f:
+        jsonstring = json.load(f)
+    d = mj.decode(jsonstring, classes=rdrone.Drone)  # jsonpickle.decode(jsonstring, classes=Drone)
+    assert type(d) is rdrone.Drone and type(d.controller) is rbrain.NeuralNetwork and type(d.sensors[0]) is rsensor.Sensor
+    assert type(d.quadcopter).__name__ == "QuadcopterPhysics" and d.quadcopter.G == 0.4 * 9.81 and d.dh.visualize is False
+    assert d.quadcopter.angle_control_to_thrust.tolist() == [[1, -1, -1], [-1, -1, 1], [-1, 1, -1], [1, 1, 1]]
+    assert all(np.array_equal(a, b) and a.dtype == np.float64 for a, b in zip(d.controller.weights, ours.controller.weights))
+    d.reset()
+    with contextlib.redirect_stdout(io.StringIO()):
+        reward, real_time, _ = ref_fly(d, idx=0)
+    assert (reward, d.flight_time, d.crashed) == (-4077, 170, True) and abs(real_time - 1.69) < 1e-12  # SURVEY §8c
+    # and the other way round through the same pickler: reference Drone -> jsonpickle text -> our loader
+    with open(tmp_path / "ref.json", "w") as f:
+        json.dump(mj.encode(d), f)
+    back = checkpoint.load_drone(tmp_path / "ref.json")
+    assert np.array_equal(back.controller.genome(), ours.controller.genome()) and back.reward == -4077
