@@ -26,7 +26,10 @@ from ..population import fly_population_device, reduce_records_device
 
 class GpuEvolution:
     def __init__(self, genomes, seed: int = 0, timesteps: int = 2500, mutation_rate: float = 0.05, p_tournament: float = 0.6,
-                 p_crossover: float = 0.05, mutation_sigma: float = 0.3, device=None, p2p=None, **fly_kw):
+                 p_crossover: float = 0.05, mutation_sigma: float = 0.3, device=None, p2p=None, local_shard: bool = False,
+                 n_global: int = None, **fly_kw):
+        """genomes: the whole (n, 314) population (same on every rank), or — local_shard=True — only this rank's
+        contiguous shard of an n_global-drone population (big populations: no rank holds the whole matrix on the host)."""
         import torch
         import torch.distributed as dist
 
@@ -38,11 +41,14 @@ class GpuEvolution:
         g = torch.as_tensor(np.ascontiguousarray(genomes, dtype=np.float64)) if not torch.is_tensor(genomes) else genomes
         if g.dim() != 2 or g.shape[1] != GENOME_LEN:
             raise ValueError(f"genomes must have shape (n, {GENOME_LEN})")
-        self.n = g.shape[0]
+        self.n = int(n_global) if local_shard else g.shape[0]
         if self.n % (2 * self.world) != 0:
             raise ValueError("population size must be a multiple of 2 x world size (pair slots, equal shards)")
         self.lo, self.hi = shard_bounds(self.n, self.rank, self.world)
         self.shard_rows = self.hi - self.lo
+        if local_shard and g.shape[0] != self.shard_rows:
+            raise ValueError(f"local shard has {g.shape[0]} rows, rank {self.rank} of {self.world} owns {self.shard_rows} of {self.n}")
+        self._local_shard = bool(local_shard)
         slice_steps = fly_kw.pop("slice_steps", None)
         self.params = make_params(timesteps=timesteps, **fly_kw)
         # Scheduling only (ld_params.slice_steps).  Offspring populations mix a few long-lived drones with many
@@ -75,7 +81,11 @@ class GpuEvolution:
                 warnings.warn(f"GpuEvolution: peer-memory GA step unavailable, using the replicated mode: {e!r}", RuntimeWarning)
         self.ga_mode = "single" if self.world == 1 else ("p2p" if self.p2p else "replicated")
         if not self.p2p:
-            self.population = g.to(self.device, dtype=torch.float64).contiguous().clone()
+            if local_shard and self.world > 1:
+                self.population = torch.empty((self.n, GENOME_LEN), dtype=torch.float64, device=self.device)
+                self.dist.all_gather_into_tensor(self.population, g.to(self.device, dtype=torch.float64).contiguous())
+            else:
+                self.population = g.to(self.device, dtype=torch.float64).contiguous().clone()
             self.next_population = torch.empty_like(self.population)
 
     # -- sharded storage in symmetric memory: peers read parent rows over NVLink --------------------
@@ -92,7 +102,7 @@ class GpuEvolution:
             self._handles.append(h)
             self._tables.append(make_peer_table([int(p) for p in h.buffer_ptrs], self.shard_rows))
         self._cur = 0
-        self._bufs[0].copy_(g[self.lo:self.hi].to(self.device, dtype=torch.float64))
+        self._bufs[0].copy_((g if self._local_shard else g[self.lo:self.hi]).to(self.device, dtype=torch.float64))
         torch.cuda.synchronize(self.device)
         self.dist.barrier()
 

@@ -8,8 +8,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 for _p in (HERE, ROOT):
     if _p not in sys.path:
         sys.path.insert(0, _p)
-if False:
-    sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -43,3 +41,21 @@ def _built_library():
     from learning_drones_b200 import build as ldbuild
 
     ldbuild.build()
+
+
+# ---- measured parity figures, printed at the end of the session (also with -q) -----------------------------------
+PARITY_REPORT = []
+
+
+@pytest.fixture(scope="session")
+def parity_report():
+    """Tests append one line per measured GPU-vs-oracle / GPU-vs-reference comparison: the number of drones whose
+    integer outcome differs, not just a bound that passed."""
+    return PARITY_REPORT.append
+
+
+def pytest_terminal_summary(terminalreporter):
+    if PARITY_REPORT:
+        terminalreporter.write_sep("-", "measured parity (drones with a differing integer outcome)")
+        for line in PARITY_REPORT:
+            terminalreporter.write_line(line)

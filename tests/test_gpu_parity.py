@@ -24,18 +24,22 @@ def gen():
 
 
 @pytest.mark.parametrize("name,kw,min_robust", SETS)
-def test_kernel_matches_reference_fixture(pop, oracle, golden, name, kw, min_robust):
+def test_kernel_matches_reference_fixture(pop, oracle, golden, parity_report, name, kw, min_robust):
     g = golden(name)
     p = make_params(int(g["timesteps"]), **kw)
     cond = conditioning(oracle, p, g["genomes"])
     rec, state = pop.fly_population_host(g["genomes"], p, want_state=True)
     robust = check_records(rec, state, g, cond, SET_STATE_FRAC.get(name))
     assert robust.mean() >= min_robust
+    differ = (rec["reward"] != g["reward"]) | (rec["flight_time"] != g["flight_time"]) | (rec["coins"] != g["coins"])
+    parity_report(f"GPU vs REFERENCE fixture {name}: {int(differ.sum())} of {len(differ)} drones differ "
+                  f"({int((differ & robust).sum())} of them well-conditioned; coin collectors differing: "
+                  f"{int((differ & (g['coins'] > 0)).sum())} of {int((g['coins'] > 0).sum())})")
 
 
 @pytest.mark.parametrize("family,n,H", [("survivors", 4096, 2000), ("random", 4096, 2000), ("random", 20000, 2500),
                                         ("survivors", 65536, 2000), ("random", 65536, 2000)])  # last two: config 3 at FULL size
-def test_kernel_matches_oracle_subsample(pop, oracle, gen, family, n, H):
+def test_kernel_matches_oracle_subsample(pop, oracle, gen, parity_report, family, n, H):
     """parity on a subsample of the config-3 populations against the CPU oracle."""
     rng = np.random.default_rng(2026)
     s = gen.survivors(65536, rng)
@@ -51,6 +55,9 @@ def test_kernel_matches_oracle_subsample(pop, oracle, gen, family, n, H):
     assert robust.mean() > 0.98
     # the ill-conditioned remainder may differ, but only rarely
     same = (rec["reward"] == ref["reward"]) & (rec["flight_time"] == ref["flight_time"])
+    parity_report(f"GPU vs oracle, {family} {n} drones x {H} steps: {int((~same).sum())} of {n} drones differ "
+                  f"({int((~same & robust).sum())} of them well-conditioned, cond < {COND_ROBUST:g}); rank order of the "
+                  f"agreeing drones identical")
     assert same.mean() > 0.995
 
 
@@ -375,7 +382,7 @@ def test_saturating_brains_and_nonfinite_status(pop, oracle, gen):
     assert rec["flight_time"].tolist() == ref["flight_time"].tolist() == [50] * 8  # NaN never crashes (drone.py:150)
 
 
-def test_kernel_matches_reference_large(pop, oracle, golden):
+def test_kernel_matches_reference_large(pop, oracle, golden, parity_report):
     """The CUDA kernel against 8,192 random drones flown by the REAL reference (results-only fixture)."""
     from test_oracle_golden import _large_fixture
 
@@ -390,6 +397,8 @@ def test_kernel_matches_reference_large(pop, oracle, golden):
     dev = np.max(np.abs(state[robust, :3] - g["position"][robust]) / (1 + np.abs(g["position"][robust])), axis=1)
     assert np.median(dev) < 1e-10 and (dev < 1e-6).mean() > 0.99
     same = (rec["reward"] == g["reward"]) & (rec["flight_time"] == g["flight_time"])
+    parity_report(f"GPU vs REFERENCE, 8192 random drones x {int(g['timesteps'])} steps flown by the real reference: {int((~same).sum())} of "
+                  f"{len(same)} drones differ ({int((~same & robust).sum())} of them well-conditioned; {int(robust.sum())} well-conditioned in all)")
     assert same.mean() > 0.995
     # fitness rank order of the whole generation (north star): identical on the robust drones
     a, b = rec["reward"][robust], g["reward"][robust]
