@@ -320,6 +320,15 @@ int ld_measure_fp64_peak(double* tflops_out, double* dfma_per_clk_per_sm_out);
  * fn 0: out0=sin(x) out1=cos(x) | 1: out0=exp(x) | 2: out0=1/(exp(-0.4x)+1) | 3: out0=x/y out1=1/y */
 int ld_debug_math_device(int fn, const double* x, const double* y, double* out0, double* out1, int64_t n, void* stream);
 
+/* Where the episode kernel spends its time (development tap): same launch as ld_fly_mlp_f64_device (no final state,
+ * no wind / payload) with an instrumented instantiation that sums, over all warps, clock64 cycles per phase and a
+ * few event counts into prof[LD_PROFILE_SLOTS] (device, zeroed by the call): 0 claim (queue atomics, slot polls),
+ * 1 stage (brain rows -> Tensor Memory / shared memory), 2 wait (nothing to fly), 3 hot loop, 4 publish / park,
+ * 5 staging events, 6 lanes staged, 7 hot-loop entries, 8 warp-steps, 9 live lane-steps, 10 warps. */
+#define LD_PROFILE_SLOTS 16
+int ld_debug_fly_profile_device(const ld_params* params, const double* genomes, int64_t n, ld_record* records,
+                                int64_t* work_counter, uint64_t* prof, void* stream);
+
 /* frees the device workspaces that the *_host entry points keep between calls (per host thread) */
 void ld_release_workspace(void);
 

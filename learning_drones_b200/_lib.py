@@ -27,6 +27,7 @@ EXPORTS = (
     "ld_release_workspace",
     "ld_measure_fp64_peak",
     "ld_debug_math_device",
+    "ld_debug_fly_profile_device",
     "ld_fly_pid_f64_device",
     "ld_fly_pid_f64_host",
     "ld_ga_step_device",
@@ -94,6 +95,8 @@ def load():
     L.ld_measure_fp64_peak.restype = C.c_int
     L.ld_debug_math_device.argtypes = [C.c_int, vp, vp, vp, vp, i64, vp]
     L.ld_debug_math_device.restype = C.c_int
+    L.ld_debug_fly_profile_device.argtypes = [C.POINTER(LdParams), dp, i64, vp, vp, vp, vp]
+    L.ld_debug_fly_profile_device.restype = C.c_int
     L.ld_fly_pid_f64_device.argtypes = [C.POINTER(LdParams), C.POINTER(LdPidParams), dp, i64, vp, dp, vp]
     L.ld_fly_pid_f64_device.restype = C.c_int
     L.ld_fly_pid_f64_host.argtypes = [C.POINTER(LdParams), C.POINTER(LdPidParams), dp, i64, vp, dp]

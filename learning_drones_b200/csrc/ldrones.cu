@@ -46,6 +46,7 @@ constexpr int kSmemUsed = kCtaThreads * kRowBytes;    // 59392
 // Tensor Memory is one allocation per SM: request more than half of the SM's shared memory so a
 // second CTA (e.g. of a concurrent launch on another stream) can never become resident next to us
 constexpr int kSmemBytes = 120 * 1024;
+static_assert(LD_PROFILE_SLOTS >= 11, "profile slots");
 static_assert(kSmemUsed <= kSmemBytes, "shared-memory rows");
 constexpr int kRefillBatch = 6;                       // idle lanes that trigger a refill
 static_assert((kRowBytes / 16) % 2 == 1, "row stride must be an odd number of 16-B units (bank-conflict-free LDS.128)");
@@ -142,7 +143,11 @@ struct Sched {
     // optional per-drone start: [n][LD_STATE_LEN] rows (pos vel angle angle_vel acc_current acc_last thrust) that
     // replace ld_params.init_* — fly() on Drones that are not in the reset state (flight/__init__.py:35-39)
     const double* init_state;
+    // debug (ld_debug_fly_profile_device): per-phase clock64 totals over all warps, see kProf*; NULL in production
+    unsigned long long* prof;
 };
+enum { kProfClaim = 0, kProfStage, kProfWait, kProfHot, kProfPost, kProfStageEvents, kProfFreshLanes, kProfHotEntries, kProfWarpSteps,
+       kProfLiveLaneSteps, kProfWarps, kProfCount };
 // a warp that has had nothing to fly and nothing become ready for this long gives up (never in a healthy run: it
 // turns a lost queue entry into an error instead of a hung GPU).  Measured from the moment the warp began to wait
 // without progress, so long launches, debuggers and time-sliced GPUs do not trip it.
@@ -381,7 +386,7 @@ __device__ __forceinline__ void stage_tmem(uint32_t taddr, bool mine_fresh, cons
 // MODE kState: also write the final kinematic state; kTrace: n == 1, dump the state after every
 // measure() (debug tap).  All 32 lanes execute every step (idle lanes run masked) so that the
 // step body is one straight-line, warp-converged block.
-template <bool EXTRAS, int MODE>
+template <bool EXTRAS, int MODE, bool PROF = false>
 __global__ void __launch_bounds__(kCtaThreads, 1)
 fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict__ genomes, long long n,
                    ld_record* __restrict__ records, double* __restrict__ final_state,
@@ -410,6 +415,14 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
     const int batch = p.refill_batch > 0 ? p.refill_batch : kRefillBatch;
 
     unsigned long long wait_since = 0; // 0 = the warp is not waiting (warp-uniform)
+    unsigned long long pf[kProfCount] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // PROF only
+    long long pt = PROF ? clock64() : 0;
+#define LD_PROF_LAP(slot)                          \
+    if (PROF) {                                    \
+        const long long now_ = clock64();          \
+        pf[slot] += (unsigned long long)(now_ - pt); \
+        pt = now_;                                 \
+    }
 
     Drone d;
     drone_reset(p, d);
@@ -452,6 +465,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             }
         }
         if (__any_sync(0xffffffffu, drained)) more = false;
+        LD_PROF_LAP(kProfClaim)
         // ---- stage the brains of the lanes that got a drone ------------------------------------------
         if (__any_sync(0xffffffffu, ready)) {
             wait_since = 0; // progress
@@ -483,6 +497,11 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             stage_tmem(taddr, ready, row);
             tmem_wait_st();
             trig_update(d); // warp-converged; recomputing it for lanes in flight is idempotent
+            if (PROF) {
+                pf[kProfStageEvents] += 1;
+                pf[kProfFreshLanes] += __popc(__ballot_sync(0xffffffffu, ready));
+            }
+            LD_PROF_LAP(kProfStage)
         }
         const unsigned flying = __ballot_sync(0xffffffffu, idx >= 0);
         if (flying == 0u) {
@@ -498,6 +517,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
                     more = false;
                 }
             }
+            LD_PROF_LAP(kProfWait)
             continue;
         }
 
@@ -522,8 +542,10 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
         }
         double a_last[6];
         bool crashed, done, big;
+        int prof_iters = 0;
         do {
             int u;
+            if (PROF) ++prof_iters;
             uint32_t w0[32];
             tmem_ld32(w0, taddr); // first 16 brain weights for this step's MLP, in flight during the physics
             step_rewards_and_coin(p, d, live, time_reward);
@@ -552,6 +574,12 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             if (big) trig_slow(d);
             if (__any_sync(0xffffffffu, done)) break;
         } while (true);
+        if (PROF) {
+            pf[kProfHotEntries] += 1;
+            pf[kProfWarpSteps] += prof_iters;
+            pf[kProfLiveLaneSteps] += (unsigned long long)prof_iters * __popc(__ballot_sync(0xffffffffu, live));
+        }
+        LD_PROF_LAP(kProfHot)
         if (done && live) {
             bool leave = true;
             if (crashed || t >= H) {
@@ -582,6 +610,15 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
                 // that a wildly tumbling leftover cannot drag the warp into the large-angle fallback branch
                 drone_reset(p, d);
             }
+        }
+        LD_PROF_LAP(kProfPost)
+    }
+#undef LD_PROF_LAP
+    if (PROF) {
+        pf[kProfWarps] = 1;
+        if (lane == 0 && q.prof) {
+#pragma unroll
+            for (int i = 0; i < kProfCount; ++i) atomicAdd(q.prof + i, pf[i]);
         }
     }
 
@@ -1211,6 +1248,7 @@ int ensure_device() {
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f64_kernel<true, kState>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f64_kernel<false, kTrace>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f64_kernel<true, kTrace>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    LD_CUDA(cudaFuncSetAttribute(fly_mlp_f64_kernel<false, kPlain, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f32_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesF32));
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f32_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesF32));
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f32_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesF32));
@@ -1264,7 +1302,7 @@ int auto_first_segment(long long n, long long lanes, int H) {
 // work_counter: int64[2] of device scratch — [0] queue head, [1] error flag (raised if a warp gave up waiting)
 int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* records, double* final_state,
                int64_t* work_counter, double* trace, cudaStream_t s, bool f32 = false,
-               const unsigned long long* arrived = nullptr, const double* init_state = nullptr) {
+               const unsigned long long* arrived = nullptr, const double* init_state = nullptr, unsigned long long* prof = nullptr) {
     int rc = ensure_device();
     if (rc) return rc;
     if (n == 0) return LD_OK;
@@ -1296,6 +1334,7 @@ int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* 
     q.arrived = arrived;
     q.error = reinterpret_cast<int*>(work_counter + 1);
     q.init_state = init_state;
+    q.prof = prof;
     // slice_steps > 0: equal segments; <= -2: segments that double in length, the first one -slice_steps long;
     // 0: automatic (doubling from H/4 when it pays); -1: off
     const bool doubling = p->slice_steps <= -2 || p->slice_steps == 0;
@@ -1321,7 +1360,10 @@ int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* 
 #define LD_LAUNCH(EX, MD) \
     fly_mlp_f64_kernel<EX, MD><<<grid, block, kSmemBytes, s>>>(*p, genomes, n, records, final_state, q, trace)
     const int mode = trace ? kTrace : (final_state ? kState : kPlain);
-    if (ex) {
+    if (prof) {
+        if (ex || mode != kPlain) return fail(LD_ERR_INVALID_ARG, "the profile build exists for the plain kernel without wind / payload / final state");
+        fly_mlp_f64_kernel<false, kPlain, true><<<grid, block, kSmemBytes, s>>>(*p, genomes, n, records, final_state, q, trace);
+    } else if (ex) {
         if (mode == kTrace) LD_LAUNCH(true, kTrace);
         else if (mode == kState) LD_LAUNCH(true, kState);
         else LD_LAUNCH(true, kPlain);
@@ -1620,6 +1662,16 @@ int ld_fly_mlp_f64_device(const ld_params* params, const double* genomes, int64_
     if ((reinterpret_cast<uintptr_t>(genomes) & 15u) || (reinterpret_cast<uintptr_t>(records) & 15u))
         return fail(LD_ERR_INVALID_ARG, "genomes and records must be 16-byte aligned");
     return launch_fly(params, genomes, n, records, final_state, work_counter, nullptr, (cudaStream_t)stream);
+}
+
+int ld_debug_fly_profile_device(const ld_params* params, const double* genomes, int64_t n, ld_record* records, int64_t* work_counter,
+                                uint64_t* prof, void* stream) {
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (n <= 0 || !genomes || !records || !work_counter || !prof) return fail(LD_ERR_INVALID_ARG, "bad arguments");
+    LD_CUDA(cudaMemsetAsync(prof, 0, LD_PROFILE_SLOTS * sizeof(uint64_t), (cudaStream_t)stream));
+    return launch_fly(params, genomes, n, records, nullptr, work_counter, nullptr, (cudaStream_t)stream, false, nullptr, nullptr,
+                      reinterpret_cast<unsigned long long*>(prof));
 }
 
 int ld_fly_mlp_f64_trace_device(const ld_params* params, const double* genome, ld_record* record, double* trace,

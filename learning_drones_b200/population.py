@@ -120,6 +120,28 @@ def check_work_counter(work_counter):
         raise _lib.LdError(-2, "episode kernel gave up waiting for its work queue; records are incomplete")
 
 
+PROFILE_SLOTS = ("claim", "stage", "wait", "hot", "post", "stage_events", "lanes_staged", "hot_entries", "warp_steps",
+                 "live_lane_steps", "warps")
+
+
+def fly_population_profile(genomes, params: LdParams = None, **kw):
+    """Development tap (ld_debug_fly_profile_device): fly `genomes` (CUDA float64 (n, 314)) with the instrumented
+    kernel and return (records, dict) — cycles per phase summed over all warps and event counts.  Synchronises."""
+    import torch
+
+    L = _lib.load()
+    p = _params(params, kw)
+    n, dev = genomes.shape[0], genomes.device
+    with torch.cuda.device(dev):
+        records = torch.empty((n, RECORD_WORDS), dtype=torch.int64, device=dev)
+        counter = torch.empty(2, dtype=torch.int64, device=dev)
+        prof = torch.zeros(16, dtype=torch.int64, device=dev)
+        _lib.check(L.ld_debug_fly_profile_device(C.byref(p), genomes.data_ptr(), n, records.data_ptr(), counter.data_ptr(), prof.data_ptr(),
+                                                 torch.cuda.current_stream(dev).cuda_stream))
+        torch.cuda.synchronize(dev)
+    return records, dict(zip(PROFILE_SLOTS, prof.cpu().tolist()))
+
+
 def records_to_numpy(records) -> np.ndarray:
     """int64[n][4] CUDA/CPU tensor -> structured numpy array (synchronises)."""
     a = records.detach().cpu().numpy()

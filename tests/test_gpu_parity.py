@@ -248,8 +248,10 @@ def test_fly_drop_in(golden):
     assert d.distance_to_coin == pytest.approx(11.208182019123052, rel=1e-9)
     np.testing.assert_allclose(d.position.ravel(), g["state"][0, :3], rtol=1e-7)
     assert d.position.shape == (3, 1) and d.thrust.shape == (4, 1)
-    with pytest.raises(RuntimeError):
-        fly(d)  # needs reset(), like evolution.py does
+    # a second fly() without reset() continues from the crashed state (z <= 0: crashes again at once) and adds to
+    # the counters, like the reference does (flight/__init__.py:35-45); evolution.py resets between generations
+    reward2, real_time2, _ = fly(d)
+    assert d.flight_time == 171 and reward2 < reward - 3000 and real_time2 == 0.0 and d.crashed
     d.reset()
     assert fly(d, idx=5)[0] == -4077
 
