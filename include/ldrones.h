@@ -324,10 +324,12 @@ int ld_debug_math_device(int fn, const double* x, const double* y, double* out0,
  * no wind / payload) with an instrumented instantiation that sums, over all warps, clock64 cycles per phase and a
  * few event counts into prof[LD_PROFILE_SLOTS] (device, zeroed by the call): 0 claim (queue atomics, slot polls),
  * 1 stage (brain rows -> Tensor Memory / shared memory), 2 wait (nothing to fly), 3 hot loop, 4 publish / park,
- * 5 staging events, 6 lanes staged, 7 hot-loop entries, 8 warp-steps, 9 live lane-steps, 10 warps. */
+ * 5 staging events, 6 lanes staged, 7 hot-loop entries, 8 warp-steps, 9 live lane-steps, 10 warps; of the staging:
+ * 11 drone state (reset / unpark), 12 row copies into shared memory, 13 Tensor-Memory / shared-memory writes, 14 groups.
+ * times (device, [n][2], may be NULL): %globaltimer ns at which every drone first got a lane and at which it landed. */
 #define LD_PROFILE_SLOTS 16
 int ld_debug_fly_profile_device(const ld_params* params, const double* genomes, int64_t n, ld_record* records,
-                                int64_t* work_counter, uint64_t* prof, void* stream);
+                                int64_t* work_counter, uint64_t* prof, uint64_t* times, void* stream);
 
 /* frees the device workspaces that the *_host entry points keep between calls (per host thread) */
 void ld_release_workspace(void);

@@ -8,7 +8,8 @@ import os
 from ._abi import LD_ABI_VERSION, LdGaParams, LdParams, LdPeerTable, LdPidParams, LdRecord
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libldrones.so")
+# LDRONES_LIB: development override (A/B builds of the kernel library); the product always loads the in-tree build
+LIB_PATH = os.environ.get("LDRONES_LIB") or os.path.join(_HERE, "libldrones.so")
 
 # every symbol include/ldrones.h declares
 EXPORTS = (
@@ -95,7 +96,7 @@ def load():
     L.ld_measure_fp64_peak.restype = C.c_int
     L.ld_debug_math_device.argtypes = [C.c_int, vp, vp, vp, vp, i64, vp]
     L.ld_debug_math_device.restype = C.c_int
-    L.ld_debug_fly_profile_device.argtypes = [C.POINTER(LdParams), dp, i64, vp, vp, vp, vp]
+    L.ld_debug_fly_profile_device.argtypes = [C.POINTER(LdParams), dp, i64, vp, vp, vp, vp, vp]
     L.ld_debug_fly_profile_device.restype = C.c_int
     L.ld_fly_pid_f64_device.argtypes = [C.POINTER(LdParams), C.POINTER(LdPidParams), dp, i64, vp, dp, vp]
     L.ld_fly_pid_f64_device.restype = C.c_int

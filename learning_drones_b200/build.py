@@ -41,13 +41,29 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-Xptxas", "-v", "-o", LIB] + SOURCES
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libldrones.so")
+    spilled = episode_kernel_spills(r.stdout + r.stderr)
+    if spilled:
+        os.remove(LIB)
+        raise RuntimeError(f"the fp64 episode kernel spills registers ({spilled}): its hot loop must stay in registers")
     return LIB
+
+
+def episode_kernel_spills(ptxas_log: str):
+    """ptxas -v lines of the fly_mlp_f64_kernel instantiations that report spill stores / loads (a spilling hot loop
+    costs 30 % — measured)."""
+    bad, current = [], None
+    for line in ptxas_log.splitlines():
+        if "Function properties for" in line or "Compiling entry function" in line:
+            current = line
+        elif "spill stores" in line and current and "fly_mlp_f64_kernel" in current and " 0 bytes spill stores, 0 bytes spill loads" not in line:
+            bad.append(line.strip())
+    return bad
 
 
 if __name__ == "__main__":

@@ -43,10 +43,22 @@ constexpr int kChunks = kTmemDoubles / kChunk;        // 16
 constexpr int kSmemDoubles = LD_GENOME_LEN - kTmemDoubles; // 58
 constexpr int kRowBytes = kSmemDoubles * 8;           // 464
 constexpr int kSmemUsed = kCtaThreads * kRowBytes;    // 59392
-// Tensor Memory is one allocation per SM: request more than half of the SM's shared memory so a
+// Brain staging: the rows of the lanes that get a new drone are copied into a per-warp staging buffer with
+// coalesced 16-B cp.async (a 2512-B row = 157 pieces), kStageRows rows at a time; the owner lanes then read their
+// row in stored order (the genome -> stored permutation costs nothing at LDS time; rows 2512 B apart are
+// bank-conflict-free for LDS.64/.128 because 157 is odd).
+#ifndef LD_STAGE_ROWS
+#define LD_STAGE_ROWS 8
+#endif
+constexpr int kStageRows = LD_STAGE_ROWS;
+constexpr int kGenomeBytes = LD_GENOME_LEN * 8;            // 2512
+constexpr int kRowPieces = kGenomeBytes / 16;              // 157
+constexpr int kStageBytesPerWarp = kStageRows * kGenomeBytes; // 20096
+static_assert(kGenomeBytes % 16 == 0 && kRowPieces % 2 == 1, "16-B pieces, odd row stride");
+// Tensor Memory is one allocation per SM: the request is more than half of the SM's shared memory, so a
 // second CTA (e.g. of a concurrent launch on another stream) can never become resident next to us
-constexpr int kSmemBytes = 120 * 1024;
-static_assert(LD_PROFILE_SLOTS >= 11, "profile slots");
+constexpr int kSmemBytes = kSmemUsed + kWarpsPerCta * kStageBytesPerWarp; // 139776
+static_assert(kSmemBytes > 116 * 1024 && kSmemBytes <= 227 * 1024, "one CTA per SM");
 static_assert(kSmemUsed <= kSmemBytes, "shared-memory rows");
 constexpr int kRefillBatch = 6;                       // idle lanes that trigger a refill
 static_assert((kRowBytes / 16) % 2 == 1, "row stride must be an odd number of 16-B units (bank-conflict-free LDS.128)");
@@ -145,9 +157,11 @@ struct Sched {
     const double* init_state;
     // debug (ld_debug_fly_profile_device): per-phase clock64 totals over all warps, see kProf*; NULL in production
     unsigned long long* prof;
+    unsigned long long* prof_times; // [n][2] globaltimer ns of every drone's first start and of its landing, or NULL
 };
 enum { kProfClaim = 0, kProfStage, kProfWait, kProfHot, kProfPost, kProfStageEvents, kProfFreshLanes, kProfHotEntries, kProfWarpSteps,
-       kProfLiveLaneSteps, kProfWarps, kProfCount };
+       kProfLiveLaneSteps, kProfWarps, kProfStageState, kProfStageCopy, kProfStageTmem, kProfStageGroups, kProfCount };
+static_assert(LD_PROFILE_SLOTS >= kProfCount, "profile slots");
 // a warp that has had nothing to fly and nothing become ready for this long gives up (never in a healthy run: it
 // turns a lost queue entry into an error instead of a hung GPU).  Measured from the moment the warp began to wait
 // without progress, so long launches, debuggers and time-sliced GPUs do not trip it.
@@ -359,28 +373,42 @@ __device__ __forceinline__ void publish(const ld_params& p, Drone& d, const doub
     }
 }
 
-// Stage the brains of the lanes in `fresh` (bit per lane): Tensor-Memory part by read-modify-write
-// of whole 16-double chunks (tcgen05.st writes all 32 lanes, so lanes in flight write back what
-// they read), shared-memory part by plain stores.  Warp-converged.
-template <int C = 0>
-__device__ __forceinline__ void stage_tmem(uint32_t taddr, bool mine_fresh, const double* __restrict__ row) {
-    if constexpr (C < kChunks) {
-        uint32_t v[32];
-        tmem_ld32(v, taddr + 32 * C);
-        tmem_wait_ld(v);
-        if (mine_fresh) {
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Tensor-Memory part of the brains of one staging group: read-modify-write of whole 16-double chunks (tcgen05.st
+// writes all 32 lanes, so lanes that keep their drone write back what they read), four chunks per round so that
+// the waits and the LDS latency are paid four times instead of sixteen.  `mine` = this lane's staged row (genome
+// order) if it is in the group.  Warp-converged.
+constexpr int kStageBatch = 2; // 4 spills the hot loop's registers (255 + 1.5 KB of spill stores): measured 30 % slower
+template <int C0 = 0>
+__device__ __forceinline__ void stage_tmem(uint32_t taddr, bool in_group, const double* __restrict__ mine) {
+    if constexpr (C0 < kChunks) {
+        uint32_t v[kStageBatch][32];
 #pragma unroll
-            for (int e = 0; e < kChunk; ++e) {
-                const double w = __ldca(row + stored_to_genome(C * kChunk + e));
-                v[2 * e] = (uint32_t)__double2loint(w);
-                v[2 * e + 1] = (uint32_t)__double2hiint(w);
+        for (int q = 0; q < kStageBatch; ++q) tmem_ld32(v[q], taddr + 32 * (C0 + q));
+#pragma unroll
+        for (int q = 0; q < kStageBatch; ++q) tmem_wait_ld(v[q]);
+        if (in_group) {
+#pragma unroll
+            for (int q = 0; q < kStageBatch; ++q) {
+#pragma unroll
+                for (int e = 0; e < kChunk; ++e) {
+                    const double w = mine[stored_to_genome((C0 + q) * kChunk + e)];
+                    v[q][2 * e] = (uint32_t)__double2loint(w);
+                    v[q][2 * e + 1] = (uint32_t)__double2hiint(w);
+                }
             }
         }
         __syncwarp();
-        tmem_st32(v, taddr + 32 * C);
-        stage_tmem<C + 1>(taddr, mine_fresh, row);
+#pragma unroll
+        for (int q = 0; q < kStageBatch; ++q) tmem_st32(v[q], taddr + 32 * (C0 + q));
+        stage_tmem<C0 + kStageBatch>(taddr, in_group, mine);
     }
 }
+static_assert(kChunks % kStageBatch == 0, "staging rounds");
 
 // One population evaluation = the loop of evolve/evolution.py:64-73 around flight/__init__.py:fly().
 // MODE kState: also write the final kinematic state; kTrace: n == 1, dump the state after every
@@ -395,6 +423,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
     __shared__ uint32_t tmem_base_slot;
     double2* wrow = reinterpret_cast<double2*>(smem_raw + (size_t)threadIdx.x * kRowBytes);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned char* stage_buf = smem_raw + kSmemUsed + (size_t)warp * kStageBytesPerWarp; // this warp's kStageRows staged rows
 
     // the CTA owns the SM's whole Tensor Memory (512 columns x 128 lanes x 32 bit = 256 KiB)
     if (warp == 0) {
@@ -415,7 +444,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
     const int batch = p.refill_batch > 0 ? p.refill_batch : kRefillBatch;
 
     unsigned long long wait_since = 0; // 0 = the warp is not waiting (warp-uniform)
-    unsigned long long pf[kProfCount] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // PROF only
+    unsigned long long pf[kProfCount] = {}; // PROF only
     long long pt = PROF ? clock64() : 0;
 #define LD_PROF_LAP(slot)                          \
     if (PROF) {                                    \
@@ -471,30 +500,71 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             wait_since = 0; // progress
             const double* __restrict__ row = genomes + who * LD_GENOME_LEN;
             if (ready) {
-                // pull the 2512-B row into L1 with 20 independent loads; the gathers below then hit
-                unsigned touch = 0;
-#pragma unroll
-                for (int i = 0; i < LD_GENOME_LEN; i += 16) touch ^= (unsigned)__double2loint(__ldca(row + i));
-                if (touch == 0x9e3779b9u) wrow[0].x = 0.0; // keeps the loads alive; rewritten just below
-#pragma unroll
-                for (int i = 0; i < kSmemDoubles / 2; ++i) {
-                    double2 w;
-                    w.x = __ldca(row + stored_to_genome(kTmemDoubles + 2 * i));
-                    w.y = __ldca(row + stored_to_genome(kTmemDoubles + 2 * i + 1));
-                    wrow[i] = w;
-                }
                 idx = who;
                 slot = -1;
                 if (resume) unpark_drone(d, q.park + who * kParkDoubles);
                 else {
                     drone_reset(p, d);
                     if (q.init_state) load_start_state(d, q.init_state + who * LD_STATE_LEN);
+                    if (PROF && q.prof_times) q.prof_times[2 * who] = globaltimer_ns();
                 }
                 t = d.flight_time;
                 t_end = min(H, q.growth * t + q.slice);
             }
-            __syncwarp();
-            stage_tmem(taddr, ready, row);
+            long long ps = PROF ? clock64() : 0; // sub-phases of the staging (PROF only)
+            if (PROF) pf[kProfStageState] += (unsigned long long)(ps - pt);
+            // brains: kStageRows lanes at a time
+            unsigned todo = __ballot_sync(0xffffffffu, ready);
+            while (todo != 0u) { // warp-uniform
+                unsigned group = 0, rest = todo;
+#pragma unroll
+                for (int j = 0; j < kStageRows; ++j) {
+                    const unsigned low = rest & (0u - rest);
+                    group |= low;
+                    rest ^= low;
+                }
+                todo = rest;
+                // coalesced asynchronous copy of the group's rows (L2 -> shared memory, no registers, one round trip)
+                unsigned g = group;
+#pragma unroll
+                for (int j = 0; j < kStageRows; ++j) {
+                    const bool have = g != 0u; // warp-uniform
+                    const int src = have ? __ffs(g) - 1 : 0;
+                    g &= g - 1u;
+                    const unsigned long long rp = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)row, src);
+                    if (have) {
+                        const uint32_t dst = smem_u32(stage_buf) + j * kGenomeBytes;
+#pragma unroll
+                        for (int i = 0; i < (kRowPieces + 31) / 32; ++i) {
+                            const int piece = (int)lane + 32 * i;
+                            if (piece < kRowPieces) cp_async16(dst + piece * 16, reinterpret_cast<const char*>(rp) + piece * 16);
+                        }
+                    }
+                }
+                cp_async_wait_all();
+                __syncwarp();
+                if (PROF) {
+                    const long long now_ = clock64();
+                    pf[kProfStageCopy] += (unsigned long long)(now_ - ps);
+                    pf[kProfStageGroups] += 1;
+                    ps = now_;
+                }
+                const bool in_group = (group >> lane) & 1u;
+                const double* __restrict__ mine =
+                    reinterpret_cast<const double*>(stage_buf + (size_t)__popc(group & ((1u << lane) - 1u)) * kGenomeBytes);
+                if (in_group) {
+#pragma unroll
+                    for (int i = 0; i < kSmemDoubles / 2; ++i)
+                        wrow[i] = make_double2(mine[stored_to_genome(kTmemDoubles + 2 * i)], mine[stored_to_genome(kTmemDoubles + 2 * i + 1)]);
+                }
+                stage_tmem(taddr, in_group, mine);
+                __syncwarp(); // everyone is done with the staged rows before the next group overwrites them
+                if (PROF) {
+                    const long long now_ = clock64();
+                    pf[kProfStageTmem] += (unsigned long long)(now_ - ps);
+                    ps = now_;
+                }
+            }
             tmem_wait_st();
             trig_update(d); // warp-converged; recomputing it for lanes in flight is idempotent
             if (PROF) {
@@ -585,6 +655,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             if (crashed || t >= H) {
                 publish<MODE>(p, d, a_last, idx, records, final_state);
                 if (q.cap) atomicAdd(q.done, 1ull);
+                if (PROF && q.prof_times) q.prof_times[2 * idx + 1] = globaltimer_ns();
             } else {
                 // segment boundary: give the lane up only if some drone is waiting for one, i.e. if the next
                 // slot to be claimed is filled (a fresh row that has arrived, or a parked drone)
@@ -1302,7 +1373,8 @@ int auto_first_segment(long long n, long long lanes, int H) {
 // work_counter: int64[2] of device scratch — [0] queue head, [1] error flag (raised if a warp gave up waiting)
 int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* records, double* final_state,
                int64_t* work_counter, double* trace, cudaStream_t s, bool f32 = false,
-               const unsigned long long* arrived = nullptr, const double* init_state = nullptr, unsigned long long* prof = nullptr) {
+               const unsigned long long* arrived = nullptr, const double* init_state = nullptr, unsigned long long* prof = nullptr,
+               unsigned long long* prof_times = nullptr) {
     int rc = ensure_device();
     if (rc) return rc;
     if (n == 0) return LD_OK;
@@ -1335,6 +1407,7 @@ int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* 
     q.error = reinterpret_cast<int*>(work_counter + 1);
     q.init_state = init_state;
     q.prof = prof;
+    q.prof_times = prof_times;
     // slice_steps > 0: equal segments; <= -2: segments that double in length, the first one -slice_steps long;
     // 0: automatic (doubling from H/4 when it pays); -1: off
     const bool doubling = p->slice_steps <= -2 || p->slice_steps == 0;
@@ -1665,13 +1738,13 @@ int ld_fly_mlp_f64_device(const ld_params* params, const double* genomes, int64_
 }
 
 int ld_debug_fly_profile_device(const ld_params* params, const double* genomes, int64_t n, ld_record* records, int64_t* work_counter,
-                                uint64_t* prof, void* stream) {
+                                uint64_t* prof, uint64_t* times, void* stream) {
     int rc = check_params(params);
     if (rc) return rc;
     if (n <= 0 || !genomes || !records || !work_counter || !prof) return fail(LD_ERR_INVALID_ARG, "bad arguments");
     LD_CUDA(cudaMemsetAsync(prof, 0, LD_PROFILE_SLOTS * sizeof(uint64_t), (cudaStream_t)stream));
     return launch_fly(params, genomes, n, records, nullptr, work_counter, nullptr, (cudaStream_t)stream, false, nullptr, nullptr,
-                      reinterpret_cast<unsigned long long*>(prof));
+                      reinterpret_cast<unsigned long long*>(prof), reinterpret_cast<unsigned long long*>(times));
 }
 
 int ld_fly_mlp_f64_trace_device(const ld_params* params, const double* genome, ld_record* record, double* trace,

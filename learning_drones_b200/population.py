@@ -121,12 +121,13 @@ def check_work_counter(work_counter):
 
 
 PROFILE_SLOTS = ("claim", "stage", "wait", "hot", "post", "stage_events", "lanes_staged", "hot_entries", "warp_steps",
-                 "live_lane_steps", "warps")
+                 "live_lane_steps", "warps", "stage_state", "stage_copy", "stage_tmem", "stage_groups")
 
 
-def fly_population_profile(genomes, params: LdParams = None, **kw):
+def fly_population_profile(genomes, params: LdParams = None, timeline: bool = False, **kw):
     """Development tap (ld_debug_fly_profile_device): fly `genomes` (CUDA float64 (n, 314)) with the instrumented
-    kernel and return (records, dict) — cycles per phase summed over all warps and event counts.  Synchronises."""
+    kernel and return (records, dict) — cycles per phase summed over all warps and event counts; with timeline=True
+    the dict also holds "times": int64 (n, 2) ns (first start, landing) relative to the earliest start.  Synchronises."""
     import torch
 
     L = _lib.load()
@@ -136,10 +137,15 @@ def fly_population_profile(genomes, params: LdParams = None, **kw):
         records = torch.empty((n, RECORD_WORDS), dtype=torch.int64, device=dev)
         counter = torch.empty(2, dtype=torch.int64, device=dev)
         prof = torch.zeros(16, dtype=torch.int64, device=dev)
+        times = torch.zeros((n, 2), dtype=torch.int64, device=dev) if timeline else None
         _lib.check(L.ld_debug_fly_profile_device(C.byref(p), genomes.data_ptr(), n, records.data_ptr(), counter.data_ptr(), prof.data_ptr(),
-                                                 torch.cuda.current_stream(dev).cuda_stream))
+                                                 times.data_ptr() if timeline else None, torch.cuda.current_stream(dev).cuda_stream))
         torch.cuda.synchronize(dev)
-    return records, dict(zip(PROFILE_SLOTS, prof.cpu().tolist()))
+    out = dict(zip(PROFILE_SLOTS, prof.cpu().tolist()))
+    if timeline:
+        t = times.cpu().numpy()
+        out["times"] = t - t[:, 0].min()
+    return records, out
 
 
 def records_to_numpy(records) -> np.ndarray:

@@ -47,7 +47,8 @@ def report(name, gt, slice_steps, batch=0):
     ev = max(f["stage_events"], 1)
     print(f"{name:34s} slice {slice_steps:5d} batch {batch:2d}: {ms:7.3f} ms  {active / ms / 1e6:7.2f} G active steps/s | "
           + " ".join(f"{k} {v:4.1f}%" for k, v in share.items())
-          + f" | stage {f['stage'] / ev:7.0f} cyc/event, {f['lanes_staged'] / ev:4.1f} lanes/event, {ev / max(f['warps'], 1):6.1f} events/warp"
+          + f" | stage {f['stage'] / ev:7.0f} cyc/event (state {f['stage_state'] / ev:5.0f}, copy {f['stage_copy'] / ev:5.0f}, tmem {f['stage_tmem'] / ev:5.0f}, "
+          + f"{f['stage_groups'] / ev:3.1f} groups), {f['lanes_staged'] / ev:4.1f} lanes/event, {ev / max(f['warps'], 1):6.1f} events/warp"
           + f" | hot: {f['hot'] / max(f['warp_steps'], 1):6.0f} cyc/warp-step, live lanes {100.0 * f['live_lane_steps'] / max(32 * f['warp_steps'], 1):4.1f}%"
           + f" | claim {f['claim'] / max(f['hot_entries'], 1):5.0f} post {f['post'] / max(f['hot_entries'], 1):5.0f} cyc/entry", flush=True)
 
@@ -60,8 +61,9 @@ off2 = ev.population.clone()
 ev.run(3)
 off5 = ev.population.clone()
 auto_ga = -max(125, H // 4)
+QUICK = os.environ.get("LD_PROFILE_QUICK") == "1"
 for name, gt, slices in (("survivors", surv, (0, -1)), ("random init", rnd, (0, -1)), ("GA offspring, generation 2", off2, (auto_ga, -1, -125)),
                          ("GA offspring, generation 5", off5, (auto_ga, -1, -125))):
-    for sl in slices:
-        for batch in ((0,) if name == "survivors" else (0, 2, 4, 8, 12)):
+    for sl in (slices[:2] if QUICK else slices):
+        for batch in ((0,) if (name == "survivors" or QUICK) else (0, 2, 4, 8, 12)):
             report(name, gt, sl, batch)
