@@ -21,6 +21,7 @@
 namespace ld {
 
 constexpr double kTrigFastMax = 105615.0;
+constexpr unsigned kTrigFastMaxHi = 0x40f9c8f0u; // high word of 105615.0 (low word 0)
 
 // Polynomial coefficients live in constant memory: a DFMA can take its addend straight from the
 // constant bank, whereas literals are rebuilt with two 32-bit moves per use inside the hot loop.
@@ -97,8 +98,11 @@ __device__ __forceinline__ double exp_fast(double x) {
     // clamp so that k stays within the two-step scaling range; exp is saturated out there anyway.
     // Written with compares (not fmin/fmax) so that a NaN stays a NaN, as in the reference where a
     // NaN thrust poisons the state and int(nan) finally raises (drone/drone.py:14).
-    const double xlo = x < -760.0 ? -760.0 : x;
-    const double xc = xlo > 760.0 ? 760.0 : xlo;
+    // Decided on the high word (integer pipe instead of two fp64 compares): |x| >= 760 (incl. +-inf) -> +-760, NaN kept.
+    const int xhi = __double2hiint(x);
+    const unsigned xabs = (unsigned)xhi & 0x7fffffffu;
+    const bool clamp = xabs >= 0x4087c000u && (xabs < 0x7ff00000u || (xabs == 0x7ff00000u && __double2loint(x) == 0));
+    const double xc = clamp ? __hiloint2double((xhi & 0x80000000) | 0x4087c000, 0) : x;
     const double q = fma(xc, kRed[4], magic);
     const int k = __double2loint(q);
     const double j = q - magic;
@@ -117,8 +121,8 @@ __device__ __forceinline__ double exp_fast(double x) {
 // brain.py:37-39 : 1 / (exp(-beta x) + 1)
 __device__ __forceinline__ double sigmoid_fast(double x, double neg_beta) {
     const double d = exp_fast(neg_beta * x) + 1.0;
-    // exp overflow: d = +inf -> exactly 0 like the reference (the Newton steps would give NaN)
-    const bool overflow = d > 1.7976931348623157e308;
+    // exp overflow: d = +inf -> exactly 0 like the reference (the Newton steps would give NaN); test on the bits
+    const bool overflow = __double2hiint(d) == 0x7ff00000 && __double2loint(d) == 0;
     const double dd = overflow ? 1.7976931348623157e308 : d; // NaN stays NaN
     const double y = div_by(1.0, dd, recip(dd));
     return overflow ? 0.0 : y;

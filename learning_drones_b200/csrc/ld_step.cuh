@@ -70,7 +70,12 @@ __device__ __forceinline__ void trig_fast(Drone& d) {
 // kernel folds `trig_is_big` into the vote that ends its hot loop and calls `trig_slow` per lane
 // outside of it.  Must run before the next physics_step.
 __device__ __forceinline__ bool trig_is_big(const Drone& d) {
-    return !(fabs(d.x[3]) <= kTrigFastMax && fabs(d.x[4]) <= kTrigFastMax && fabs(d.x[5]) <= kTrigFastMax);
+    // !(|angle| <= kTrigFastMax) for any of the three angles, NaN included, decided on the high words (integer pipe):
+    // kTrigFastMax = 105615.0 has a zero low word, and the fast reduction is valid well beyond it, so an angle whose
+    // high word equals the bound's is still handled by the straight-line path.
+    const unsigned a = (unsigned)__double2hiint(d.x[3]) & 0x7fffffffu, b = (unsigned)__double2hiint(d.x[4]) & 0x7fffffffu,
+                   c = (unsigned)__double2hiint(d.x[5]) & 0x7fffffffu;
+    return max(a, max(b, c)) > kTrigFastMaxHi;
 }
 
 __device__ __forceinline__ void trig_slow(Drone& d) {
