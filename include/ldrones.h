@@ -325,7 +325,8 @@ int ld_debug_math_device(int fn, const double* x, const double* y, double* out0,
  * few event counts into prof[LD_PROFILE_SLOTS] (device, zeroed by the call): 0 claim (queue atomics, slot polls),
  * 1 stage (brain rows -> Tensor Memory / shared memory), 2 wait (nothing to fly), 3 hot loop, 4 publish / park,
  * 5 staging events, 6 lanes staged, 7 hot-loop entries, 8 warp-steps, 9 live lane-steps, 10 warps; of the staging:
- * 11 drone state (reset / unpark), 12 row copies into shared memory, 13 Tensor-Memory / shared-memory writes, 14 groups.
+ * 11 drone state (reset / unpark), 12 row copies into shared memory, 13 Tensor-Memory / shared-memory writes, 14 groups, 15 warp-steps that ran the
+ * large-angle (libm) trigonometry.
  * times (device, [n][2], may be NULL): %globaltimer ns at which every drone first got a lane and at which it landed. */
 #define LD_PROFILE_SLOTS 16
 int ld_debug_fly_profile_device(const ld_params* params, const double* genomes, int64_t n, ld_record* records,

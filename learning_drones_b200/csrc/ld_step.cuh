@@ -75,7 +75,11 @@ __device__ __forceinline__ bool trig_is_big(const Drone& d) {
     // high word equals the bound's is still handled by the straight-line path.
     const unsigned a = (unsigned)__double2hiint(d.x[3]) & 0x7fffffffu, b = (unsigned)__double2hiint(d.x[4]) & 0x7fffffffu,
                    c = (unsigned)__double2hiint(d.x[5]) & 0x7fffffffu;
+#ifdef LD_DIAG_NO_SLOW_TRIG // timing diagnostic only (wrong results beyond the bound)
+    return false;
+#else
     return max(a, max(b, c)) > kTrigFastMaxHi;
+#endif
 }
 
 __device__ __forceinline__ void trig_slow(Drone& d) {
@@ -143,8 +147,13 @@ __device__ __forceinline__ void step_rewards_and_coin(const ld_params& p, Drone&
 // (physical_model.py:93-120) + 6x Sensor.measure_acceleration/velocity_verlet
 // (sensor.py:42-49,62-73,85-93) + crash rule.  `rcp_m` = 1 / double(m_total32).
 // Returns true when the crash box is left; `unstable` gets the number of -1 penalties.
+// `dt` = ld_params.dt for a lane that flies a drone.  The episode kernel passes 0 for lanes without one: all lanes
+// execute every step, and a lane that waits for its next drone would otherwise fly a "ghost" of the reset state with
+// the previous drone's brain — tumbling for thousands of steps until its angles leave the fast trigonometric range and
+// drag the whole warp through the libm branch on every step (measured: 8.5 % of the warp-steps and 17 % of the kernel
+// time of a GA generation).  With dt = 0 the ghost stays at the finite reset state.
 template <bool EXTRAS>
-__device__ __forceinline__ bool physics_step(const ld_params& p, Drone& d, double rcp_m, double* a_last_out, int& unstable) {
+__device__ __forceinline__ bool physics_step(const ld_params& p, Drone& d, double rcp_m, double* a_last_out, int& unstable, double dt) {
     const Trig& g = d.trig;
     const double sr = g.sr, cr = g.cr, sp = g.sp, cp = g.cp, sy = g.sy, cy = g.cy;
     // B = Rz.(Ry.Rx); rotation_matrix() returns B^T.  Zero/one entries folded (exact).
@@ -202,7 +211,7 @@ __device__ __forceinline__ bool physics_step(const ld_params& p, Drone& d, doubl
     // integrator, expressions as sensor.py:63-72 (old velocity in delta_x).  0.5*a*dt*dt is
     // evaluated as (a*dt)*(0.5*dt) and 0.5*(a0+a1)*dt as (a0+a1)*(0.5*dt): scaling by 0.5 is
     // exact, so both are bit-identical to the reference's left-to-right products.
-    const double dt = p.dt, hdt = 0.5 * p.dt;
+    const double hdt = 0.5 * dt;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         const double a_last = d.acc[i];

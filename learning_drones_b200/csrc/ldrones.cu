@@ -160,7 +160,7 @@ struct Sched {
     unsigned long long* prof_times; // [n][2] globaltimer ns of every drone's first start and of its landing, or NULL
 };
 enum { kProfClaim = 0, kProfStage, kProfWait, kProfHot, kProfPost, kProfStageEvents, kProfFreshLanes, kProfHotEntries, kProfWarpSteps,
-       kProfLiveLaneSteps, kProfWarps, kProfStageState, kProfStageCopy, kProfStageTmem, kProfStageGroups, kProfCount };
+       kProfLiveLaneSteps, kProfWarps, kProfStageState, kProfStageCopy, kProfStageTmem, kProfStageGroups, kProfSlowTrigSteps, kProfCount };
 static_assert(LD_PROFILE_SLOTS >= kProfCount, "profile slots");
 // a warp that has had nothing to fly and nothing become ready for this long gives up (never in a healthy run: it
 // turns a lost queue entry into an error instead of a hung GPU).  Measured from the moment the warp began to wait
@@ -610,6 +610,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             t = 0;
             t_end = kPollSteps;
         }
+        const double dt_lane = live ? p.dt : 0.0; // lanes without a drone do not move (see physics_step)
         double a_last[6];
         bool crashed, done, big;
         int prof_iters = 0;
@@ -619,7 +620,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             uint32_t w0[32];
             tmem_ld32(w0, taddr); // first 16 brain weights for this step's MLP, in flight during the physics
             step_rewards_and_coin(p, d, live, time_reward);
-            crashed = physics_step<EXTRAS>(p, d, rcp_m, MODE != kPlain ? a_last : nullptr, u) && live;
+            crashed = physics_step<EXTRAS>(p, d, rcp_m, MODE != kPlain ? a_last : nullptr, u, dt_lane) && live;
             d.reward += crashed ? p.reward_crashed : ((live ? u : 0) * p.reward_unstable);
             d.unstable += (live && !crashed) ? u : 0;
             d.status |= crashed ? LD_STATUS_CRASHED : 0;
@@ -642,6 +643,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             big = trig_is_big(d);
             if (!__any_sync(0xffffffffu, done || big)) continue;
             if (big) trig_slow(d);
+            if (PROF) pf[kProfSlowTrigSteps] += __any_sync(0xffffffffu, big) ? 1 : 0;
             if (__any_sync(0xffffffffu, done)) break;
         } while (true);
         if (PROF) {
@@ -959,7 +961,7 @@ fly_pid_f64_kernel(const __grid_constant__ ld_params p, const __grid_constant__ 
         for (int k = 0; k < 3; ++k) set[k] = q.coin_pos[target][k];
         // :328-341 — physics + integrator (no crash rule in this script)
         int u;
-        physics_step<EXTRAS>(p, d, rcp_m, a_last, u);
+        physics_step<EXTRAS>(p, d, rcp_m, a_last, u, p.dt);
         trig_update(d);
         // drone/onboard_computer.py:50-85 — cascaded PIDs
         double lin_out[3], rot_out[3];
@@ -1157,7 +1159,7 @@ drone_step_kernel(const __grid_constant__ ld_params p, int what, const double* _
         trig_update(d); // warp-converged: every thread of the block gets here
         double a_last[6];
         int u;
-        const bool crashed = physics_step<EXTRAS>(p, d, 1.0 / (double)p.m_total32, a_last, u);
+        const bool crashed = physics_step<EXTRAS>(p, d, 1.0 / (double)p.m_total32, a_last, u, p.dt);
         if (exists) {
             write_state(d, a_last, row);
             flags[2 * i] = crashed ? 1 : 0;

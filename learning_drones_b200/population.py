@@ -121,7 +121,7 @@ def check_work_counter(work_counter):
 
 
 PROFILE_SLOTS = ("claim", "stage", "wait", "hot", "post", "stage_events", "lanes_staged", "hot_entries", "warp_steps",
-                 "live_lane_steps", "warps", "stage_state", "stage_copy", "stage_tmem", "stage_groups")
+                 "live_lane_steps", "warps", "stage_state", "stage_copy", "stage_tmem", "stage_groups", "slow_trig_steps")
 
 
 def fly_population_profile(genomes, params: LdParams = None, timeline: bool = False, **kw):

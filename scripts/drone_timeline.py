@@ -50,3 +50,15 @@ for slice_steps in (-1, -500, -125):
     edges = np.arange(0, land.max() + 100, 100)
     occ = [(int(((start <= e) & (land > e)).sum())) for e in edges]
     print("   drones between start and landing every 100 us:", occ, flush=True)
+    print(f"   warp-steps {f['warp_steps']}, of them through the large-angle libm trigonometry: {f['slow_trig_steps']} ({100.0 * f['slow_trig_steps'] / max(f['warp_steps'], 1):.2f} %)")
+    if slice_steps == -1:
+        _, st = pop.fly_population_device(gt, p, want_state=True)
+        ang = np.abs(st.cpu().numpy()[:, 6:9]).max(axis=1)
+        status = pop.records_to_numpy(rec)["status"]
+        print(f"   non-finite drones (status bit 2): {int(((status & 2) != 0).sum())}, of them flying the whole horizon: {int((((status & 2) != 0) & full).sum())}; "
+              f"non-finite final angles: {int((~np.isfinite(ang)).sum())}")
+        big = ang > 105615.0
+        dur = land - start
+        print(f"   drones that end beyond the fast trigonometric range (|angle| > 1.05e5 rad): {int(big.sum())} of {D}, {int((big & full).sum())} of them "
+              f"full-horizon; |angle| quantiles of full-horizon drones p50/p90/p99/max {q(ang[full])}; stretch of full-horizon drones with / without a "
+              f"big final angle: {np.median(dur[full & big]) / (H * step_us) if (full & big).any() else float('nan'):.3f} / {np.median(dur[full & ~big]) / (H * step_us):.3f}", flush=True)
