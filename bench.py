@@ -564,7 +564,9 @@ def main():
                     "per_rank_seconds": e2e_all,
                     "h2d_gbs_per_rank_concurrent": h2d_all,
                     "limiter": "host->device copy of the genome rows: every rank streams its own pinned buffer through the host at the "
-                               "same time (h2d_gbs_per_rank_concurrent is that leg alone); kernel time is `ms_per_step`",
+                               "same time; h2d_gbs_per_rank_concurrent is that leg alone (one rank alone reaches ~55 GB/s; on the 8-GPU "
+                               "box four GPUs behind one host bridge got 23 GB/s each and the other four 36 GB/s, whatever cores the ranks "
+                               "were bound to — profiles/r02_bench_n8*.json); kernel time is `ms_per_step`",
                     "binding": binding},
             "gpu_launches": args.steps * world,
             "clocks": m["clocks"],

@@ -11,6 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libldrones.so")
+# the same library with the episode kernel's own bounds checks compiled in (-DLD_CHECKED); tests/test_gpu_soak.py runs it
+LIB_CHECKED = os.path.join(HERE, "libldrones_checked.so")
 SOURCES = [os.path.join(CSRC, "ldrones.cu")]
 DEPS = SOURCES + [os.path.join(CSRC, h) for h in ("ld_step.cuh", "ld_math.cuh", "ld_f32.cuh")] + [os.path.join(ROOT, "include", "ldrones.h")]
 
@@ -32,17 +34,23 @@ def nvcc_path() -> str:
 
 
 def is_stale() -> bool:
-    if not os.path.exists(LIB):
+    if not (os.path.exists(LIB) and os.path.exists(LIB_CHECKED)):
         return True
-    t = os.path.getmtime(LIB)
+    t = min(os.path.getmtime(LIB), os.path.getmtime(LIB_CHECKED))
     return any(os.path.getmtime(f) > t for f in DEPS)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
+    checked = subprocess.Popen([nvcc_path()] + NVCC_FLAGS + ["-DLD_CHECKED", "-o", LIB_CHECKED] + SOURCES, stdout=subprocess.PIPE,
+                               stderr=subprocess.STDOUT, text=True)  # in parallel with the product build
     cmd = [nvcc_path()] + NVCC_FLAGS + ["-Xptxas", "-v", "-o", LIB] + SOURCES
     r = subprocess.run(cmd, capture_output=True, text=True)
+    checked_out, _ = checked.communicate()
+    if checked.returncode != 0:
+        sys.stderr.write(checked_out)
+        raise RuntimeError("nvcc failed building libldrones_checked.so")
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:

@@ -167,6 +167,21 @@ static_assert(LD_PROFILE_SLOTS >= kProfCount, "profile slots");
 // without progress, so long launches, debuggers and time-sliced GPUs do not trip it.
 constexpr unsigned long long kWaitLimitNs = 20ull * 1000 * 1000 * 1000;
 
+// Checked build (-DLD_CHECKED -> libldrones_checked.so, run by tests/test_gpu_soak.py): compute-sanitizer is closed on
+// this GPU pool, so the index arithmetic of the queue / park / re-queue / staging protocol carries its own bounds
+// checks; a violation ORs a code into the launch's error word (work_counter[1]), which every entry point reports.
+#ifdef LD_CHECKED
+#define LD_CHECK(cond, code)                 \
+    do {                                     \
+        if (!(cond)) atomicOr(q.error, code); \
+    } while (0)
+#else
+#define LD_CHECK(cond, code) \
+    do {                     \
+    } while (0)
+#endif
+enum { kErrGaveUp = 1, kErrSlotRange = 2, kErrDroneRange = 4, kErrRequeueOverflow = 8, kErrPublishRange = 16, kErrStageSlot = 32 };
+
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -471,6 +486,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             base = __shfl_sync(0xffffffffu, base, leader);
             const long long mine = (long long)base + __popc(idle & ((1u << lane) - 1u));
             if ((idle >> lane) & 1u) slot = mine < n_slots ? mine : -1;
+            LD_CHECK(slot < n_slots, kErrSlotRange);
             more = (long long)base + __popc(idle) < n_slots;
         }
         // ---- whose slot is filled? -------------------------------------------------------------------
@@ -493,6 +509,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
                 }
             }
         }
+        LD_CHECK(!ready || (who >= 0 && who < n), kErrDroneRange);
         if (__any_sync(0xffffffffu, drained)) more = false;
         LD_PROF_LAP(kProfClaim)
         // ---- stage the brains of the lanes that got a drone ------------------------------------------
@@ -550,6 +567,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
                     ps = now_;
                 }
                 const bool in_group = (group >> lane) & 1u;
+                LD_CHECK(__popc(group) <= kStageRows && __popc(group & ((1u << lane) - 1u)) < kStageRows + (in_group ? 0 : 32), kErrStageSlot);
                 const double* __restrict__ mine =
                     reinterpret_cast<const double*>(stage_buf + (size_t)__popc(group & ((1u << lane) - 1u)) * kGenomeBytes);
                 if (in_group) {
@@ -582,7 +600,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
                 const unsigned long long now = globaltimer_ns();
                 if (wait_since == 0) wait_since = now;
                 else if (now - wait_since > kWaitLimitNs) {
-                    *q.error = 1; // reported by the host entry points and through work_counter[1] of the device API
+                    atomicOr(q.error, (int)kErrGaveUp); // reported by the host entry points and through work_counter[1] of the device API
                     slot = -1;
                     more = false;
                 }
@@ -654,6 +672,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
         LD_PROF_LAP(kProfHot)
         if (done && live) {
             bool leave = true;
+            LD_CHECK(idx >= 0 && idx < n, kErrPublishRange);
             if (crashed || t >= H) {
                 publish<MODE>(p, d, a_last, idx, records, final_state);
                 if (q.cap) atomicAdd(q.done, 1ull);
@@ -671,6 +690,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
                     park_drone(d, q.park + idx * kParkDoubles);
                     __threadfence();
                     const unsigned long long at = atomicAdd(q.tail, 1ull);
+                    LD_CHECK((long long)at < q.cap, kErrRequeueOverflow);
                     st_release(q.requeue + at, (int)idx + 1);
                 } else {
                     t_end = min(H, q.growth * t + q.slice);
@@ -1618,7 +1638,11 @@ int fly_streamed_batch(const ld_params* params, const double* genomes, const dou
     LD_CUDA(cudaMemcpyAsync(w.h_error, w.ctl + 2, sizeof(int), cudaMemcpyDeviceToHost, w.compute));
     LD_CUDA(cudaStreamSynchronize(w.copy));
     LD_CUDA(cudaStreamSynchronize(w.compute));
-    if (*w.h_error) return fail(LD_ERR_CUDA, "episode kernel gave up waiting for its work queue");
+    if (*w.h_error) {
+        snprintf(g_err, sizeof(g_err), "episode kernel error word %d (1 = gave up waiting for its work queue; >= 2 = bounds check of a checked build)",
+                 *w.h_error);
+        return LD_ERR_CUDA;
+    }
     return LD_OK;
 }
 

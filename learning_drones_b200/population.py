@@ -116,8 +116,10 @@ def fly_population_device(genomes, params: LdParams = None, want_state: bool = F
 def check_work_counter(work_counter):
     """After the launch has completed: raise if the episode kernel gave up waiting for its work queue
     (work_counter[1], see include/ldrones.h).  Synchronises."""
-    if int(work_counter[1].item()) != 0:
-        raise _lib.LdError(-2, "episode kernel gave up waiting for its work queue; records are incomplete")
+    word = int(work_counter[1].item()) & 0xFFFFFFFF
+    if word != 0:
+        raise _lib.LdError(-2, f"episode kernel error word {word} (1 = gave up waiting for its work queue; >= 2 = a bounds check of the "
+                               "checked build failed); records are incomplete")
 
 
 PROFILE_SLOTS = ("claim", "stage", "wait", "hot", "post", "stage_events", "lanes_staged", "hot_entries", "warp_steps",

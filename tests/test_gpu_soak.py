@@ -48,3 +48,48 @@ def test_segment_queue_soak():
         assert same, f"run {runs}: n={n} H={H} slice={p.slice_steps} batch={p.refill_batch}"
         runs += 1
     print(f"soak: {runs} randomised runs bit-identical in {time.time() - t0:.1f} s")
+
+
+def test_soak_with_the_kernels_own_bounds_checks():
+    """The same kind of run through libldrones_checked.so (-DLD_CHECKED): slot / drone / re-queue / publish / staging
+    indices are range-checked inside the kernel and a violation is reported through the launch's error word.  Runs in a
+    subprocess because a process binds one build of the library."""
+    import os
+    import subprocess
+    import sys
+
+    from learning_drones_b200 import build as ldbuild
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from learning_drones_b200 import _lib, population as pop
+from learning_drones_b200._abi import make_params
+from oracle import gen_golden as G
+assert _lib.LIB_PATH.endswith("libldrones_checked.so")
+wave = int(_lib.load().ld_wave_size())
+rng = np.random.default_rng(77)
+pool = np.concatenate([G.survivors(2 * wave, rng), G.random_brains(2 * wave, rng)])
+for run in range(10):
+    n = int(rng.integers(wave + 1, 4 * wave))
+    g = pool[rng.permutation(len(pool))[:n]]
+    H = int(rng.integers(30, 300))
+    p = make_params(H)
+    p.slice_steps = -1
+    ref, _ = pop.fly_population_host(g, p)
+    p.slice_steps = int(rng.integers(2, H)) * (1 if run % 2 else -1)
+    p.refill_batch = int(rng.integers(0, 33))
+    out, _ = pop.fly_population_host(g, p)          # raises LdError if the kernel's error word is set
+    assert out.tobytes() == ref.tobytes(), run
+    gt = torch.from_numpy(g).cuda()
+    cnt = torch.empty(2, dtype=torch.int64, device="cuda")
+    rec, _ = pop.fly_population_device(gt, p, work_counter=cnt)
+    torch.cuda.synchronize()
+    pop.check_work_counter(cnt)
+    assert pop.records_to_numpy(rec).tobytes() == ref.tobytes(), run
+print("checked soak ok")
+""" % root
+    env = dict(os.environ, LDRONES_LIB=ldbuild.LIB_CHECKED)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "checked soak ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
