@@ -63,7 +63,7 @@ def test_soak_with_the_kernels_own_bounds_checks():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = r"""
 import sys, numpy as np, torch
-sys.path.insert(0, %r)
+sys.path.insert(0, ROOT_DIR)
 from learning_drones_b200 import _lib, population as pop
 from learning_drones_b200._abi import make_params
 from oracle import gen_golden as G
@@ -89,7 +89,7 @@ for run in range(10):
     pop.check_work_counter(cnt)
     assert pop.records_to_numpy(rec).tobytes() == ref.tobytes(), run
 print("checked soak ok")
-""" % root
+""".replace("ROOT_DIR", repr(root))
     env = dict(os.environ, LDRONES_LIB=ldbuild.LIB_CHECKED)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "checked soak ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
