@@ -434,6 +434,25 @@ def main():
         e2e_rank_s = time.perf_counter() - t0
         e2e_s = max_over_ranks(e2e_rank_s)
         assert out_np.tobytes() == rec_np.tobytes(), "host-API result differs from device-API result"
+        # the same through the pipelined host API (depth 2: step k+1's rows stream in while step k flies); every step's
+        # host->device copy and result read are inside the timed region here too
+        pipe_s = None
+        if prec == "f64":
+            outs = [torch.empty((Dl, 4), dtype=torch.int64).pin_memory().numpy().view(RECORD_DTYPE).reshape(-1) for _ in range(2)]
+            warm = [ldpop.fly_population_host_submit(host_np, params, out=outs[i]) for i in range(2)]  # warm: allocates BOTH workspaces
+            for w_ in warm:
+                w_.result()
+            barrier()
+            t0 = time.perf_counter()
+            pending = None
+            for k in range(steps):
+                nxt = ldpop.fly_population_host_submit(host_np, params, out=outs[k & 1])
+                if pending is not None:
+                    _ = int(pending.result()[0]["reward"].max())
+                pending = nxt
+            _ = int(pending.result()[0]["reward"].max())
+            pipe_s = max_over_ranks(time.perf_counter() - t0)
+            assert outs[(steps - 1) & 1].tobytes() == rec_np.tobytes(), "pipelined host-API result differs"
         # the host->device leg on its own, every rank at the same time (names the end-to-end limiter at N > 1)
         barrier()
         h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -444,7 +463,7 @@ def main():
         torch.cuda.synchronize()
         h2d_gbs = 3 * Dl * GENOME_BYTES / (h0.elapsed_time(h1) * 1e-3) / 1e9
         return dict(total_ms=total_ms, kernel_ms=kernel_ms, active=active, e2e_s=e2e_s, e2e_rank_s=e2e_rank_s, clocks=clocks,
-                    h2d_gbs=h2d_gbs, drones_local=Dl)
+                    h2d_gbs=h2d_gbs, drones_local=Dl, pipe_s=pipe_s)
 
     def gather_floats(x):
         if world == 1:
@@ -503,7 +522,8 @@ def main():
                    "value": m4["active"] * 5 / (m4["total_ms"] * 1e-3), "unit": UNIT, "ms_per_step": m4["total_ms"] / 5, "steps": 5, "warmup": 3,
                    "kernel_ms": m4["kernel_ms"], "active_drone_steps_per_step": m4["active"],
                    "e2e": {"value": m4["active"] * 5 / m4["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": CONFIG4_DRONES * GENOME_BYTES,
-                           "d2h_bytes_per_step": CONFIG4_DRONES * RECORD_BYTES},
+                           "d2h_bytes_per_step": CONFIG4_DRONES * RECORD_BYTES,
+                           "pipelined_value": None if m4["pipe_s"] is None else m4["active"] * 5 / m4["pipe_s"]},
                    "north_star_target": 1e10}
         evo = GpuEvolution(random_shard(D4, rank), seed=2026, timesteps=H, local_shard=True, n_global=CONFIG4_DRONES)
         g5 = args.config5_generations
@@ -561,6 +581,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": D * GENOME_BYTES * world,
                     "d2h_bytes_per_step": D * RECORD_BYTES * world,
                     "api": "ld_fly_mlp_f64_host via fly_population_host (one persistent launch; genome rows stream in behind it)",
+                    "pipelined": (None if m["pipe_s"] is None else
+                                  {"value": m["active"] * args.steps / m["pipe_s"], "unit": UNIT,
+                                   "api": "ld_fly_mlp_f64_host_submit / _wait via fly_population_host_submit, two submissions in flight: step "
+                                          "k+1's host->device copy overlaps step k's kernel; same bytes per step, every step's result read on "
+                                          "the host.  For jobs that evaluate independent populations back to back; `value` above is one "
+                                          "blocking call at a time"}),
                     "per_rank_seconds": e2e_all,
                     "h2d_gbs_per_rank_concurrent": h2d_all,
                     "limiter": "host->device copy of the genome rows: every rank streams its own pinned buffer through the host at the "

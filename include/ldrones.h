@@ -183,6 +183,18 @@ int ld_fly_mlp_f64_from_host(const ld_params* params, const double* genomes, con
 int ld_fly_mlp_f64_from_device(const ld_params* params, const double* genomes, const double* init_state, int64_t n,
                                ld_record* records, double* final_state, int64_t* work_counter, void* stream);
 
+/* Pipelined form of the host-buffer call, for jobs that evaluate one population after another (islands, parameter
+ * sweeps, batches of a population that does not fit one launch): `submit` queues the copies and the launch and
+ * returns at once with a ticket; `wait` blocks until that submission's records (and final_state) are in the caller's
+ * buffers and reports its status.  Up to LD_HOST_PIPELINE_DEPTH submissions may be in flight per host thread: while
+ * one flies, the next one's genome rows are already streaming in, so a step costs max(kernel, copy) instead of their
+ * sum.  Caller buffers (pinned for real overlap) must stay valid and untouched until `wait` returns; tickets belong to
+ * the submitting thread; init_state may be NULL.  1 <= n <= 4 Mi drones per submission. */
+#define LD_HOST_PIPELINE_DEPTH 2
+int ld_fly_mlp_f64_host_submit(const ld_params* params, const double* genomes, const double* init_state, int64_t n,
+                               ld_record* records, double* final_state, int64_t* ticket);
+int ld_fly_mlp_f64_host_wait(int64_t ticket);
+
 /* fp32 FAST MODE: same call contract and the same fp64 genome matrix / record
  * layout, but state, brain and arithmetic are float32 on the device.  The dynamics are chaotic:
  * float32 changes the integer outcome of a large fraction of random drones, so this

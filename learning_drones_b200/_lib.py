@@ -21,6 +21,8 @@ EXPORTS = (
     "ld_fly_mlp_f64_host",
     "ld_fly_mlp_f64_from_host",
     "ld_fly_mlp_f64_from_device",
+    "ld_fly_mlp_f64_host_submit",
+    "ld_fly_mlp_f64_host_wait",
     "ld_brain_forward_host",
     "ld_activation_host",
     "ld_fly_mlp_f64_trace_device",
@@ -75,6 +77,10 @@ def load():
     L.ld_fly_mlp_f64_from_host.restype = C.c_int
     L.ld_fly_mlp_f64_from_device.argtypes = [C.POINTER(LdParams), dp, dp, i64, vp, dp, vp, vp]
     L.ld_fly_mlp_f64_from_device.restype = C.c_int
+    L.ld_fly_mlp_f64_host_submit.argtypes = [C.POINTER(LdParams), dp, dp, i64, vp, dp, C.POINTER(C.c_int64)]
+    L.ld_fly_mlp_f64_host_submit.restype = C.c_int
+    L.ld_fly_mlp_f64_host_wait.argtypes = [i64]
+    L.ld_fly_mlp_f64_host_wait.restype = C.c_int
     L.ld_brain_forward_host.argtypes = [C.POINTER(C.c_int32), C.c_int32, dp, i64, dp, i64, dp, C.c_double]
     L.ld_brain_forward_host.restype = C.c_int
     L.ld_activation_host.argtypes = [C.c_int, dp, i64, dp, C.c_double, C.c_double]

@@ -1541,66 +1541,80 @@ struct StreamWs {
     size_t cap_drones = 0, cap_state = 0, cap_init = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t armed = nullptr;
+    bool in_flight = false;  // a submission has been enqueued and not yet waited for
+    long long sequence = 0;  // ticket check of the pipelined entry points
 };
-thread_local StreamWs g_sws;
+// Two workspaces per host thread: while one submission's kernel runs, the next one's genome rows stream into the
+// other (ld_fly_mlp_f64_host_submit / _wait, and the batches of a population larger than one launch).
+constexpr int kHostPipelineDepth = 2;
+thread_local StreamWs g_sws_slots[kHostPipelineDepth];
+static_assert(kHostPipelineDepth == LD_HOST_PIPELINE_DEPTH, "header constant");
 
-void sws_release() {
-    if (g_sws.genomes) cudaFree(g_sws.genomes);
-    if (g_sws.records) cudaFree(g_sws.records);
-    if (g_sws.state) cudaFree(g_sws.state);
-    if (g_sws.init) cudaFree(g_sws.init);
-    if (g_sws.ctl) cudaFree(g_sws.ctl);
-    if (g_sws.h_counts) cudaFreeHost(g_sws.h_counts);
-    if (g_sws.h_error) cudaFreeHost(g_sws.h_error);
-    if (g_sws.compute) cudaStreamDestroy(g_sws.compute);
-    if (g_sws.copy) cudaStreamDestroy(g_sws.copy);
-    if (g_sws.armed) cudaEventDestroy(g_sws.armed);
-    g_sws = StreamWs();
+void sws_release_slot(StreamWs& w) {
+    if (w.genomes) cudaFree(w.genomes);
+    if (w.records) cudaFree(w.records);
+    if (w.state) cudaFree(w.state);
+    if (w.init) cudaFree(w.init);
+    if (w.ctl) cudaFree(w.ctl);
+    if (w.h_counts) cudaFreeHost(w.h_counts);
+    if (w.h_error) cudaFreeHost(w.h_error);
+    if (w.compute) cudaStreamDestroy(w.compute);
+    if (w.copy) cudaStreamDestroy(w.copy);
+    if (w.armed) cudaEventDestroy(w.armed);
+    w = StreamWs();
 }
 
-int sws_reserve(size_t drones, bool want_state, bool want_init = false) {
+void sws_release() {
+    for (int i = 0; i < kHostPipelineDepth; ++i) sws_release_slot(g_sws_slots[i]);
+}
+
+int sws_reserve(StreamWs& w, size_t drones, bool want_state, bool want_init = false) {
     int dev = 0;
     LD_CUDA(cudaGetDevice(&dev));
-    if (g_sws.device != dev) {
-        sws_release();
-        LD_CUDA(cudaMalloc((void**)&g_sws.ctl, 4 * sizeof(unsigned long long)));
-        LD_CUDA(cudaHostAlloc((void**)&g_sws.h_counts, kHostChunksMax * sizeof(unsigned long long), cudaHostAllocDefault));
-        LD_CUDA(cudaHostAlloc((void**)&g_sws.h_error, sizeof(int), cudaHostAllocDefault));
-        LD_CUDA(cudaStreamCreateWithFlags(&g_sws.compute, cudaStreamNonBlocking));
-        LD_CUDA(cudaStreamCreateWithFlags(&g_sws.copy, cudaStreamNonBlocking));
-        LD_CUDA(cudaEventCreateWithFlags(&g_sws.armed, cudaEventDisableTiming));
-        g_sws.device = dev;
+    if (w.device != dev) {
+        sws_release_slot(w);
+        LD_CUDA(cudaMalloc((void**)&w.ctl, 4 * sizeof(unsigned long long)));
+        LD_CUDA(cudaHostAlloc((void**)&w.h_counts, kHostChunksMax * sizeof(unsigned long long), cudaHostAllocDefault));
+        LD_CUDA(cudaHostAlloc((void**)&w.h_error, sizeof(int), cudaHostAllocDefault));
+        LD_CUDA(cudaStreamCreateWithFlags(&w.compute, cudaStreamNonBlocking));
+        LD_CUDA(cudaStreamCreateWithFlags(&w.copy, cudaStreamNonBlocking));
+        LD_CUDA(cudaEventCreateWithFlags(&w.armed, cudaEventDisableTiming));
+        w.device = dev;
     }
-    if (g_sws.cap_drones < drones) {
-        if (g_sws.genomes) cudaFree(g_sws.genomes);
-        if (g_sws.records) cudaFree(g_sws.records);
-        if (g_sws.state) cudaFree(g_sws.state);
-        if (g_sws.init) cudaFree(g_sws.init);
-        g_sws.genomes = nullptr; g_sws.records = nullptr; g_sws.state = nullptr; g_sws.init = nullptr;
-        g_sws.cap_drones = g_sws.cap_state = g_sws.cap_init = 0;
-        LD_CUDA(cudaMalloc((void**)&g_sws.genomes, drones * LD_GENOME_LEN * sizeof(double)));
-        LD_CUDA(cudaMalloc((void**)&g_sws.records, drones * sizeof(ld_record)));
-        g_sws.cap_drones = drones;
+    if (w.cap_drones < drones) {
+        if (w.genomes) cudaFree(w.genomes);
+        if (w.records) cudaFree(w.records);
+        if (w.state) cudaFree(w.state);
+        if (w.init) cudaFree(w.init);
+        w.genomes = nullptr; w.records = nullptr; w.state = nullptr; w.init = nullptr;
+        w.cap_drones = w.cap_state = w.cap_init = 0;
+        LD_CUDA(cudaMalloc((void**)&w.genomes, drones * LD_GENOME_LEN * sizeof(double)));
+        LD_CUDA(cudaMalloc((void**)&w.records, drones * sizeof(ld_record)));
+        w.cap_drones = drones;
     }
-    if (want_state && g_sws.cap_state < drones) {
-        if (g_sws.state) cudaFree(g_sws.state);
-        g_sws.state = nullptr; g_sws.cap_state = 0;
-        LD_CUDA(cudaMalloc((void**)&g_sws.state, g_sws.cap_drones * LD_STATE_LEN * sizeof(double)));
-        g_sws.cap_state = g_sws.cap_drones;
+    if (want_state && w.cap_state < drones) {
+        if (w.state) cudaFree(w.state);
+        w.state = nullptr; w.cap_state = 0;
+        LD_CUDA(cudaMalloc((void**)&w.state, w.cap_drones * LD_STATE_LEN * sizeof(double)));
+        w.cap_state = w.cap_drones;
     }
-    if (want_init && g_sws.cap_init < drones) {
-        if (g_sws.init) cudaFree(g_sws.init);
-        g_sws.init = nullptr; g_sws.cap_init = 0;
-        LD_CUDA(cudaMalloc((void**)&g_sws.init, g_sws.cap_drones * LD_STATE_LEN * sizeof(double)));
-        g_sws.cap_init = g_sws.cap_drones;
+    if (want_init && w.cap_init < drones) {
+        if (w.init) cudaFree(w.init);
+        w.init = nullptr; w.cap_init = 0;
+        LD_CUDA(cudaMalloc((void**)&w.init, w.cap_drones * LD_STATE_LEN * sizeof(double)));
+        w.cap_init = w.cap_drones;
     }
     return LD_OK;
 }
 
-// one launch over rows [0, m) of the host matrix `genomes`
-int fly_streamed_batch(const ld_params* params, const double* genomes, const double* init_state, int64_t m, ld_record* records,
-                       double* final_state) {
-    StreamWs& w = g_sws;
+// the blocking and the secondary *_host entry points work on slot 0
+int sws_reserve(size_t drones, bool want_state, bool want_init = false) { return sws_reserve(g_sws_slots[0], drones, want_state, want_init); }
+
+// One launch over rows [0, m) of the host matrix `genomes`, in two halves: `enqueue` queues every copy and the
+// kernel on the workspace's streams and returns; `finish` waits for the records to be in the caller's buffers.
+int fly_streamed_enqueue(StreamWs& w, const ld_params* params, const double* genomes, const double* init_state, int64_t m,
+                         ld_record* records, double* final_state) {
+    if (w.in_flight) return fail(LD_ERR_INVALID_ARG, "host workspace busy: wait for the submission in flight first");
     const int64_t wave = (int64_t)g_dev.sms * kCtaThreads;
     // chunks: eighths of a wave (2368 drones = 5.9 MB, the first lanes start after ~0.1 ms) until the first
     // wave is in, then half waves (every chunk costs one extra 8-byte copy on the copy engine)
@@ -1625,25 +1639,43 @@ int fly_streamed_batch(const ld_params* params, const double* genomes, const dou
         w.h_counts[k] = (unsigned long long)off;
         LD_CUDA(cudaMemcpyAsync(w.ctl, w.h_counts + k, sizeof(unsigned long long), cudaMemcpyHostToDevice, w.copy));
     }
+    w.in_flight = true; // from here on `finish` must run before the caller's buffers may go away
     int rc = launch_fly(params, w.genomes, m, w.records, final_state ? w.state : nullptr, reinterpret_cast<int64_t*>(w.ctl + 1),
                         nullptr, w.compute, false, w.ctl, init_state ? w.init : nullptr);
-    if (rc) { // do not return while copies from the caller's buffers are still queued
-        cudaStreamSynchronize(w.copy);
-        cudaStreamSynchronize(w.compute);
-        return rc;
-    }
+    if (rc) return rc;
     LD_CUDA(cudaMemcpyAsync(records, w.records, (size_t)m * sizeof(ld_record), cudaMemcpyDeviceToHost, w.compute));
     if (final_state)
         LD_CUDA(cudaMemcpyAsync(final_state, w.state, (size_t)m * LD_STATE_LEN * sizeof(double), cudaMemcpyDeviceToHost, w.compute));
     LD_CUDA(cudaMemcpyAsync(w.h_error, w.ctl + 2, sizeof(int), cudaMemcpyDeviceToHost, w.compute));
-    LD_CUDA(cudaStreamSynchronize(w.copy));
-    LD_CUDA(cudaStreamSynchronize(w.compute));
+    return LD_OK;
+}
+
+int fly_streamed_finish(StreamWs& w) {
+    if (!w.in_flight) return LD_OK;
+    const cudaError_t e1 = cudaStreamSynchronize(w.copy), e2 = cudaStreamSynchronize(w.compute);
+    w.in_flight = false;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(LD_ERR_CUDA, "host-buffer episode launch", e1 != cudaSuccess ? e1 : e2);
     if (*w.h_error) {
         snprintf(g_err, sizeof(g_err), "episode kernel error word %d (1 = gave up waiting for its work queue; >= 2 = bounds check of a checked build)",
                  *w.h_error);
         return LD_ERR_CUDA;
     }
     return LD_OK;
+}
+
+// blocking form; on an enqueue error nothing may still read the caller's buffers when we return
+int fly_streamed_batch(StreamWs& w, const ld_params* params, const double* genomes, const double* init_state, int64_t m,
+                       ld_record* records, double* final_state) {
+    const int rc = fly_streamed_enqueue(w, params, genomes, init_state, m, records, final_state);
+    if (rc) {
+        if (w.in_flight) {
+            cudaStreamSynchronize(w.copy);
+            cudaStreamSynchronize(w.compute);
+            w.in_flight = false;
+        }
+        return rc;
+    }
+    return fly_streamed_finish(w);
 }
 
 // grow-only device scratch of the secondary *_host entry points (per host thread): no allocation per call
@@ -1804,11 +1836,35 @@ static int fly_mlp_host_impl(const ld_params* params, const double* genomes, con
     if (rc) return rc;
     if (!f32) {
         const int64_t batch = n < kHostBatchMax ? n : kHostBatchMax;
-        rc = sws_reserve((size_t)batch, final_state != nullptr, init_state != nullptr);
-        for (int64_t off = 0; off < n && rc == LD_OK; off += batch)
-            rc = fly_streamed_batch(params, genomes + off * LD_GENOME_LEN, init_state ? init_state + off * LD_STATE_LEN : nullptr,
-                                    (n - off < batch) ? (n - off) : batch, records + off,
-                                    final_state ? final_state + off * LD_STATE_LEN : nullptr);
+        for (int i = 0; i < kHostPipelineDepth; ++i)
+            if (g_sws_slots[i].in_flight) return fail(LD_ERR_INVALID_ARG, "a pipelined submission is in flight on this thread: wait for it first");
+        if (n <= batch) {
+            rc = sws_reserve((size_t)batch, final_state != nullptr, init_state != nullptr);
+            if (rc) return rc;
+            return fly_streamed_batch(g_sws_slots[0], params, genomes, init_state, n, records, final_state);
+        }
+        // a population larger than one launch: batches alternate between the two workspaces, so batch k+1's rows
+        // stream in while batch k flies
+        int slot = 0;
+        for (int64_t off = 0; off < n && rc == LD_OK; off += batch, slot ^= 1) {
+            StreamWs& w = g_sws_slots[slot];
+            rc = fly_streamed_finish(w); // the batch that used this workspace two rounds ago
+            if (rc == LD_OK) rc = sws_reserve(w, (size_t)batch, final_state != nullptr, init_state != nullptr);
+            if (rc == LD_OK)
+                rc = fly_streamed_enqueue(w, params, genomes + off * LD_GENOME_LEN, init_state ? init_state + off * LD_STATE_LEN : nullptr,
+                                          (n - off < batch) ? (n - off) : batch, records + off,
+                                          final_state ? final_state + off * LD_STATE_LEN : nullptr);
+        }
+        for (int i = 0; i < kHostPipelineDepth; ++i) {
+            StreamWs& w = g_sws_slots[i];
+            if (w.in_flight && rc != LD_OK) { // error path: drain without overwriting the first error
+                cudaStreamSynchronize(w.copy);
+                cudaStreamSynchronize(w.compute);
+                w.in_flight = false;
+            } else if (rc == LD_OK) {
+                rc = fly_streamed_finish(w);
+            }
+        }
         return rc;
     }
     // fp32 mode: pipeline over kHostStreams streams / buffers.  A chunk is a quarter of a wave (37 of 148 SMs):
@@ -1849,6 +1905,42 @@ int ld_fly_mlp_f64_host(const ld_params* params, const double* genomes, int64_t 
 int ld_fly_mlp_f64_from_host(const ld_params* params, const double* genomes, const double* init_state, int64_t n, ld_record* records,
                              double* final_state) {
     return fly_mlp_host_impl(params, genomes, init_state, n, records, final_state, false);
+}
+
+int ld_fly_mlp_f64_host_submit(const ld_params* params, const double* genomes, const double* init_state, int64_t n, ld_record* records,
+                               double* final_state, int64_t* ticket) {
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (!ticket) return fail(LD_ERR_INVALID_ARG, "NULL ticket");
+    if (n <= 0 || n > kHostBatchMax) return fail(LD_ERR_INVALID_ARG, "submit takes 1 .. 4 Mi drones per submission");
+    if (!genomes || !records) return fail(LD_ERR_INVALID_ARG, "NULL host buffer");
+    rc = ensure_device();
+    if (rc) return rc;
+    int slot = -1;
+    for (int i = 0; i < kHostPipelineDepth && slot < 0; ++i)
+        if (!g_sws_slots[i].in_flight) slot = i;
+    if (slot < 0) return fail(LD_ERR_INVALID_ARG, "pipeline full: LD_HOST_PIPELINE_DEPTH submissions are in flight, wait for one");
+    StreamWs& w = g_sws_slots[slot];
+    rc = sws_reserve(w, (size_t)n, final_state != nullptr, init_state != nullptr);
+    if (rc) return rc;
+    rc = fly_streamed_enqueue(w, params, genomes, init_state, n, records, final_state);
+    if (rc) {
+        if (w.in_flight) {
+            cudaStreamSynchronize(w.copy);
+            cudaStreamSynchronize(w.compute);
+            w.in_flight = false;
+        }
+        return rc;
+    }
+    *ticket = (++w.sequence << 8) | slot;
+    return LD_OK;
+}
+
+int ld_fly_mlp_f64_host_wait(int64_t ticket) {
+    const int slot = (int)(ticket & 0xff);
+    if (slot < 0 || slot >= kHostPipelineDepth || g_sws_slots[slot].sequence != (ticket >> 8) || !g_sws_slots[slot].in_flight)
+        return fail(LD_ERR_INVALID_ARG, "unknown or already completed ticket (tickets belong to the submitting host thread)");
+    return fly_streamed_finish(g_sws_slots[slot]);
 }
 
 int ld_fly_mlp_f64_from_device(const ld_params* params, const double* genomes, const double* init_state, int64_t n, ld_record* records,
@@ -1954,7 +2046,7 @@ int ld_fly_pid_f64_host(const ld_params* params, const ld_pid_params* pid, const
     if ((rc = scratch_get(1, (size_t)n * LD_PID_GAINS * sizeof(double), (void**)&d_gains))) return rc;
     if ((rc = scratch_get(2, (size_t)n * sizeof(ld_record), (void**)&d_rec))) return rc;
     if (final_state && (rc = scratch_get(3, (size_t)n * LD_STATE_LEN * sizeof(double), (void**)&d_state))) return rc;
-    cudaStream_t s = g_sws.compute;
+    cudaStream_t s = g_sws_slots[0].compute;
     cudaError_t e = cudaMemcpyAsync(d_gains, pid_gains, (size_t)n * LD_PID_GAINS * sizeof(double), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) rc = ld_fly_pid_f64_device(params, pid, d_gains, n, d_rec, d_state, s);
     if (e == cudaSuccess && rc == LD_OK) e = cudaMemcpyAsync(records, d_rec, (size_t)n * sizeof(ld_record), cudaMemcpyDeviceToHost, s);
@@ -2025,7 +2117,7 @@ int ld_drone_step_host(const ld_params* params, int what, const double* genomes,
         if ((rc = scratch_get(3, (size_t)n * LD_GENOME_LEN * sizeof(double), (void**)&d_gen))) return rc;
         if ((rc = scratch_get(4, (size_t)n * 3 * sizeof(double), (void**)&d_coin))) return rc;
     }
-    cudaStream_t s = g_sws.compute;
+    cudaStream_t s = g_sws_slots[0].compute;
     cudaError_t e = cudaMemcpyAsync(d_state, state, (size_t)n * LD_STATE_LEN * sizeof(double), cudaMemcpyHostToDevice, s);
     if (what == 2) {
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_gen, genomes, (size_t)n * LD_GENOME_LEN * sizeof(double), cudaMemcpyHostToDevice, s);
@@ -2069,7 +2161,7 @@ int ld_brain_forward_host(const int32_t* layer_sizes, int32_t n_layers, const do
     if ((rc = scratch_get(1, (size_t)n_brains * (weights_stride ? weights_stride : total) * sizeof(double), (void**)&d_w))) return rc;
     if ((rc = scratch_get(2, (size_t)n * n_in * sizeof(double), (void**)&d_x))) return rc;
     if ((rc = scratch_get(3, (size_t)n * n_out * sizeof(double), (void**)&d_y))) return rc;
-    cudaStream_t s = g_sws.compute;
+    cudaStream_t s = g_sws_slots[0].compute;
     cudaError_t e = cudaMemcpyAsync(d_w, weights, (size_t)n_brains * (weights_stride ? weights_stride : total) * sizeof(double),
                                     cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, inputs, (size_t)n * n_in * sizeof(double), cudaMemcpyHostToDevice, s);
@@ -2092,7 +2184,7 @@ int ld_activation_host(int kind, const double* x, int64_t n, double* out, double
     double *d_x = nullptr, *d_y = nullptr;
     if ((rc = scratch_get(1, (size_t)n * sizeof(double), (void**)&d_x))) return rc;
     if ((rc = scratch_get(2, (size_t)n * sizeof(double), (void**)&d_y))) return rc;
-    cudaStream_t s = g_sws.compute;
+    cudaStream_t s = g_sws_slots[0].compute;
     cudaError_t e = cudaMemcpyAsync(d_x, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) {
         long long blocks = (n + 255) / 256;

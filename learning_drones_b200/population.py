@@ -61,6 +61,50 @@ def fly_population_host(genomes, params: LdParams = None, want_state: bool = Fal
     return rec, st
 
 
+class HostSubmission:
+    """A population submitted with `fly_population_host_submit`; `.result()` waits for it."""
+
+    def __init__(self, ticket, genomes, records, state, init_state):
+        self._ticket, self._done = ticket, False
+        self._keep = (genomes, init_state)  # the library reads these until the wait returns
+        self.records, self.state = records, state
+
+    def result(self):
+        """(records, state|None) once they are in host memory; raises LdError if the launch failed."""
+        if not self._done:
+            self._done = True
+            _lib.check(_lib.load().ld_fly_mlp_f64_host_wait(self._ticket))
+            self._keep = None
+        return self.records, self.state
+
+
+def fly_population_host_submit(genomes, params: LdParams = None, want_state: bool = False, out=None, init_state=None, **kw) -> HostSubmission:
+    """Pipelined form of `fly_population_host` (ld_fly_mlp_f64_host_submit / _wait): returns at once; up to two
+    submissions may be in flight per thread, and while one flies the next one's rows are already streaming to the GPU
+    (a step then costs max(kernel, copy) instead of their sum).  For jobs that evaluate one population after another;
+    a dependent generation loop keeps the population on the device instead (`evolve.gpu.GpuEvolution`).
+    `genomes` / `out` should be pinned host memory for the copies to overlap."""
+    L = _lib.load()
+    p = _params(params, kw)
+    g = np.ascontiguousarray(genomes, dtype=np.float64)
+    if g.ndim != 2 or g.shape[1] != GENOME_LEN:
+        raise ValueError(f"genomes must have shape (n, {GENOME_LEN}), got {g.shape}")
+    n = g.shape[0]
+    rec = np.empty(n, dtype=RECORD_DTYPE) if out is None else out
+    if rec.dtype != RECORD_DTYPE or rec.shape != (n,) or not rec.flags.c_contiguous:
+        raise ValueError("`out` must be a contiguous RECORD_DTYPE array of length n")
+    st = np.empty((n, STATE_LEN), dtype=np.float64) if want_state else None
+    s0 = None
+    if init_state is not None:
+        s0 = np.ascontiguousarray(init_state, dtype=np.float64)
+        if s0.shape != (n, STATE_LEN):
+            raise ValueError(f"init_state must have shape ({n}, {STATE_LEN}), got {s0.shape}")
+    ticket = C.c_int64(0)
+    _lib.check(L.ld_fly_mlp_f64_host_submit(C.byref(p), g.ctypes.data, s0.ctypes.data if s0 is not None else None, n, rec.ctypes.data,
+                                            st.ctypes.data if want_state else None, C.byref(ticket)))
+    return HostSubmission(ticket.value, g, rec, st, s0)
+
+
 # ---- device tensors (torch owns the memory) ---------------------------------------------------
 def fly_population_device(genomes, params: LdParams = None, want_state: bool = False, records=None, state=None,
                           work_counter=None, precision: str = "f64", init_state=None, **kw):

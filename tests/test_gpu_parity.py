@@ -75,6 +75,43 @@ def test_trace_matches_oracle(pop, oracle, golden):
         assert tr[0, 14] == otr[0, 14]  # float32 fingerprint of step 0 is bit-exact
 
 
+def test_pipelined_host_submissions(pop, gen):
+    """ld_fly_mlp_f64_host_submit / _wait: two submissions in flight per thread, results identical to the blocking call
+    whatever the order of the waits; a third submission, a stale ticket and a blocking call in between are refused."""
+    from learning_drones_b200._lib import LdError
+
+    rng = np.random.default_rng(21)
+    pops = [np.concatenate([gen.survivors(9000, rng), gen.random_brains(15000 + 1000 * i, rng)]) for i in range(5)]
+    p = make_params(500)
+    want = [pop.fly_population_host(g, p, want_state=True) for g in pops]
+    a = pop.fly_population_host_submit(pops[0], p, want_state=True)
+    b = pop.fly_population_host_submit(pops[1], p, want_state=True)
+    with pytest.raises(LdError):
+        pop.fly_population_host_submit(pops[2], p)       # pipeline full
+    with pytest.raises(LdError):
+        pop.fly_population_host(pops[2], p)              # the blocking call needs the pipeline drained
+    rb, sb = b.result()                                  # waits may come in any order
+    ra, sa = a.result()
+    assert ra.tobytes() == want[0][0].tobytes() and rb.tobytes() == want[1][0].tobytes()
+    assert np.array_equal(sa, want[0][1]) and np.array_equal(sb, want[1][1])
+    assert a.result()[0] is ra                           # idempotent
+    # steady-state pipeline: submit k+1, then collect k
+    pending, got = None, []
+    for g in pops:
+        nxt = pop.fly_population_host_submit(g, p)
+        if pending is not None:
+            got.append(pending.result()[0])
+        pending = nxt
+    got.append(pending.result()[0])
+    assert [r.tobytes() for r in got] == [w[0].tobytes() for w in want]
+    assert pop.fly_population_host(pops[0], p)[0].tobytes() == want[0][0].tobytes()  # drained: blocking call works again
+    import ctypes as C
+
+    from learning_drones_b200 import _lib
+
+    assert _lib.load().ld_fly_mlp_f64_host_wait(C.c_int64(12345 << 8)) != 0    # unknown ticket
+
+
 def test_device_api_equals_host_api(pop, gen):
     import torch
 
