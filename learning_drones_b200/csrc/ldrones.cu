@@ -53,7 +53,12 @@ constexpr int kSmemUsed = kCtaThreads * kRowBytes;    // 59392
 constexpr int kStageRows = LD_STAGE_ROWS;
 constexpr int kGenomeBytes = LD_GENOME_LEN * 8;            // 2512
 constexpr int kRowPieces = kGenomeBytes / 16;              // 157
-constexpr int kStageBytesPerWarp = kStageRows * kGenomeBytes; // 20096
+#ifndef LD_STAGE_BUFFERS
+#define LD_STAGE_BUFFERS 1 // 2 (220 KB of shared memory): the next group's rows arrive while this group's are written — a whole-warp
+#endif                     // hand-over drops from 27.5k to 22-24k cycles, but the headline kernel gets 1.1 % SLOWER (7.08 vs 7.00 ms)
+constexpr int kStageBuffers = LD_STAGE_BUFFERS;
+constexpr int kStageGroupBytes = kStageRows * kGenomeBytes;   // 20096
+constexpr int kStageBytesPerWarp = kStageBuffers * kStageGroupBytes;
 static_assert(kGenomeBytes % 16 == 0 && kRowPieces % 2 == 1, "16-B pieces, odd row stride");
 // Tensor Memory is one allocation per SM: the request is more than half of the SM's shared memory, so a
 // second CTA (e.g. of a concurrent launch on another stream) can never become resident next to us
@@ -391,7 +396,9 @@ __device__ __forceinline__ void publish(const ld_params& p, Drone& d, const doub
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Tensor-Memory part of the brains of one staging group: read-modify-write of whole 16-double chunks (tcgen05.st
 // writes all 32 lanes, so lanes that keep their drone write back what they read), four chunks per round so that
@@ -530,18 +537,20 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             }
             long long ps = PROF ? clock64() : 0; // sub-phases of the staging (PROF only)
             if (PROF) pf[kProfStageState] += (unsigned long long)(ps - pt);
-            // brains: kStageRows lanes at a time
-            unsigned todo = __ballot_sync(0xffffffffu, ready);
-            while (todo != 0u) { // warp-uniform
-                unsigned group = 0, rest = todo;
+            // brains: kStageRows lanes at a time; with two staging buffers the next group's rows are requested before
+            // this group's are written to Tensor Memory
+            auto take_group = [](unsigned& todo) {
+                unsigned group = 0;
 #pragma unroll
                 for (int j = 0; j < kStageRows; ++j) {
-                    const unsigned low = rest & (0u - rest);
+                    const unsigned low = todo & (0u - todo);
                     group |= low;
-                    rest ^= low;
+                    todo ^= low;
                 }
-                todo = rest;
-                // coalesced asynchronous copy of the group's rows (L2 -> shared memory, no registers, one round trip)
+                return group;
+            };
+            // coalesced asynchronous copy of a group's rows (L2 -> shared memory, no registers, one round trip)
+            auto request_rows = [&](unsigned group, int buf) {
                 unsigned g = group;
 #pragma unroll
                 for (int j = 0; j < kStageRows; ++j) {
@@ -550,7 +559,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
                     g &= g - 1u;
                     const unsigned long long rp = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)row, src);
                     if (have) {
-                        const uint32_t dst = smem_u32(stage_buf) + j * kGenomeBytes;
+                        const uint32_t dst = smem_u32(stage_buf) + buf * kStageGroupBytes + j * kGenomeBytes;
 #pragma unroll
                         for (int i = 0; i < (kRowPieces + 31) / 32; ++i) {
                             const int piece = (int)lane + 32 * i;
@@ -558,7 +567,25 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
                         }
                     }
                 }
-                cp_async_wait_all();
+                cp_async_commit();
+            };
+            unsigned todo = __ballot_sync(0xffffffffu, ready);
+            unsigned group = take_group(todo);
+            int buf = 0;
+            request_rows(group, 0);
+            while (group != 0u) { // warp-uniform
+                unsigned next = 0;
+                if (kStageBuffers > 1) {
+                    next = take_group(todo);
+                    if (next != 0u) {
+                        request_rows(next, buf ^ 1);
+                        cp_async_wait_group<1>(); // everything but the group just requested
+                    } else {
+                        cp_async_wait_group<0>();
+                    }
+                } else {
+                    cp_async_wait_group<0>();
+                }
                 __syncwarp();
                 if (PROF) {
                     const long long now_ = clock64();
@@ -568,19 +595,26 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
                 }
                 const bool in_group = (group >> lane) & 1u;
                 LD_CHECK(__popc(group) <= kStageRows && __popc(group & ((1u << lane) - 1u)) < kStageRows + (in_group ? 0 : 32), kErrStageSlot);
-                const double* __restrict__ mine =
-                    reinterpret_cast<const double*>(stage_buf + (size_t)__popc(group & ((1u << lane) - 1u)) * kGenomeBytes);
+                const double* __restrict__ mine = reinterpret_cast<const double*>(
+                    stage_buf + (size_t)buf * kStageGroupBytes + (size_t)__popc(group & ((1u << lane) - 1u)) * kGenomeBytes);
                 if (in_group) {
 #pragma unroll
                     for (int i = 0; i < kSmemDoubles / 2; ++i)
                         wrow[i] = make_double2(mine[stored_to_genome(kTmemDoubles + 2 * i)], mine[stored_to_genome(kTmemDoubles + 2 * i + 1)]);
                 }
                 stage_tmem(taddr, in_group, mine);
-                __syncwarp(); // everyone is done with the staged rows before the next group overwrites them
+                __syncwarp(); // everyone is done with this buffer before it is requested again
                 if (PROF) {
                     const long long now_ = clock64();
                     pf[kProfStageTmem] += (unsigned long long)(now_ - ps);
                     ps = now_;
+                }
+                if (kStageBuffers > 1) {
+                    group = next;
+                    buf ^= 1;
+                } else {
+                    group = take_group(todo);
+                    if (group != 0u) request_rows(group, 0);
                 }
             }
             tmem_wait_st();
