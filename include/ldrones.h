@@ -36,6 +36,7 @@ extern "C" {
 #endif
 
 #define LD_ABI_VERSION 3
+#define LD_SLICE_STAGGER (-1000000) /* ld_params.slice_steps */
 
 /* brain shape fixed by drone/drone.py:65 : NeuralNetwork({1:10, 2:10, 3:4}), n_inputs=15 */
 #define LD_N_IN 15
@@ -126,7 +127,12 @@ typedef struct ld_params {
                               > 0: equal segments of this many steps; <= -2: segments that double in length,
                               the first one -slice_steps steps long; 0 = library default (doubling from
                               timesteps/4 for populations of 1..16 waves); -1 = off (every drone keeps its lane
-                              until its episode ends) */
+                              until its episode ends); LD_SLICE_STAGGER = staggered first wave, for populations
+                              known to consist of full-horizon drones: only the first batch of every warp has a
+                              boundary, spread evenly over the horizon across the warps, so the lanes run out of phase
+                              and the drones parked there fill the end of the launch longest-remaining-first —
+                              one hand-over per lane instead of two per drone (device-resident launches; a
+                              host-buffer launch, whose lanes start as their rows arrive, uses the default) */
     int32_t reserved0;
 } ld_params;
 

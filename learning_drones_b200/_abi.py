@@ -13,6 +13,7 @@ import numpy as np
 from .drone.quadcopter import parameters as P
 
 LD_ABI_VERSION = 3
+SLICE_STAGGER = -1000000  # ld_params.slice_steps = LD_SLICE_STAGGER
 N_IN, N_H1, N_H2, N_OUT = 15, 10, 10, 4
 LAYER_SHAPES = ((N_H1, N_IN + 1), (N_H2, N_H1 + 1), (N_OUT, N_H2 + 1))
 GENOME_LEN = sum(r * c for r, c in LAYER_SHAPES)  # 314

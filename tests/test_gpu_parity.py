@@ -132,7 +132,7 @@ def test_device_api_equals_host_api(pop, gen):
     assert rec_p.tobytes() == rec_h[perm].tobytes()
 
 
-@pytest.mark.parametrize("slice_steps", [0, 64, 150, 599, 4000, -40])
+@pytest.mark.parametrize("slice_steps", [0, 64, 150, 599, 4000, -40, -1000000])  # the last one = LD_SLICE_STAGGER
 def test_episode_segments_do_not_change_results(pop, gen, slice_steps):
     """ld_params.slice_steps is scheduling only: with more drones than lanes, drones are parked at segment
     boundaries and resumed on other lanes — records and final states stay bit-identical to the unsegmented run."""
