@@ -38,6 +38,8 @@ def test_segment_queue_soak():
         p.slice_steps = int(rng.integers(1, H + 20)) * (1 if rng.random() < 0.6 else -1)
         if p.slice_steps == -1:
             p.slice_steps = -2
+        if runs % 5 == 4:
+            p.slice_steps = -1000000  # LD_SLICE_STAGGER
         p.refill_batch = int(rng.integers(0, 33))
         if runs % 3 == 0:
             out, _ = pop.fly_population_host(genomes, p)
@@ -78,7 +80,7 @@ for run in range(10):
     p = make_params(H)
     p.slice_steps = -1
     ref, _ = pop.fly_population_host(g, p)
-    p.slice_steps = int(rng.integers(2, H)) * (1 if run % 2 else -1)
+    p.slice_steps = -1000000 if run % 4 == 3 else int(rng.integers(2, H)) * (1 if run % 2 else -1)   # -1000000 = LD_SLICE_STAGGER
     p.refill_batch = int(rng.integers(0, 33))
     out, _ = pop.fly_population_host(g, p)          # raises LdError if the kernel's error word is set
     assert out.tobytes() == ref.tobytes(), run

@@ -31,6 +31,19 @@ def test_library_exports_every_declared_symbol():
     assert L.ld_abi_version() == _abi.LD_ABI_VERSION
 
 
+def test_header_constants_match_the_python_binding():
+    hdr = open(os.path.join(ROOT, "include", "ldrones.h")).read()
+    macro = lambda name: int(re.search(rf"#define\s+{name}\s+\(?(-?\d+)\)?", hdr).group(1))
+    assert macro("LD_ABI_VERSION") == _abi.LD_ABI_VERSION
+    assert macro("LD_SLICE_STAGGER") == _abi.SLICE_STAGGER
+    assert macro("LD_STATE_LEN") == _abi.STATE_LEN and macro("LD_PID_GAINS") == _abi.PID_GAINS
+    assert macro("LD_MAX_PEERS") == _abi.MAX_PEERS and macro("LD_PID_MAX_COINS") == _abi.PID_MAX_COINS
+    assert macro("LD_HOST_PIPELINE_DEPTH") == 2 and macro("LD_PROFILE_SLOTS") >= 16
+    from learning_drones_b200.population import PROFILE_SLOTS
+
+    assert len(PROFILE_SLOTS) <= macro("LD_PROFILE_SLOTS")
+
+
 def test_struct_layout_matches_header():
     # sizes implied by include/ldrones.h (doubles 8-aligned, explicit pads)
     assert C.sizeof(LdRecord) == 32
