@@ -3,7 +3,7 @@
 # histogram (scripts/sass_hist.py).  usage: sass_hot_loop.sh [lib.so] [out.sass]
 LIB=${1:-learning_drones_b200/libldrones.so}
 OUT=${2:-/tmp/fly_plain.sass}
-FN=$(cuobjdump -sass "$LIB" 2>/dev/null | grep "Function" | grep "fly_mlp_f64_kernelILb0ELi0ELb0ELb0E" | sed 's/.*Function : //')
+FN=$(cuobjdump -sass "$LIB" 2>/dev/null | grep "Function" | grep "fly_mlp_f64_kernelILb0ELi0ELb0E" | head -1 | sed 's/.*Function : //')
 cuobjdump -sass -fun "$FN" "$LIB" > "$OUT" 2>&1
 RANGE=$(python3 - "$OUT" <<'PY'
 import re, sys
