@@ -20,6 +20,13 @@ b = GpuEvolution(genomes, seed=5, timesteps=500, p2p=False)
 ha, hb = a.run(6), b.run(6)
 pa, pb = a.gather_population(), b.gather_population()
 ok = ha == hb and np.array_equal(pa, pb) and np.array_equal(a.best_genome(), b.best_genome()) and a.p2p and not b.p2p
+# the same with every rank passing only its own shard (big populations: bench.py's config 5), both GA modes
+lo, hi = a.lo, a.hi
+c = GpuEvolution(genomes[lo:hi], seed=5, timesteps=500, p2p=True, local_shard=True, n_global=len(genomes))
+d = GpuEvolution(genomes[lo:hi], seed=5, timesteps=500, p2p=False, local_shard=True, n_global=len(genomes))
+hc, hd = c.run(6), d.run(6)
+ok = ok and hc == ha and hd == ha and np.array_equal(c.gather_population(), pa) and np.array_equal(d.gather_population(), pa)
+ok = ok and (a.ga_mode, b.ga_mode, c.ga_mode, d.ga_mode) == ("p2p", "replicated", "p2p", "replicated")
 if dist.get_rank() == 0:
     print("p2p == replicated:", ok, "best", ha[-1]["global_best_score"], [h["best_score"] for h in ha])
 dist.barrier()
