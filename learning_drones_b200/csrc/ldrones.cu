@@ -34,15 +34,30 @@ using namespace ld;
 // s < 256 sits in Tensor Memory: lane = the thread's TMEM lane, columns 2s (low word), 2s+1 (high
 // word); read per step as 16 tcgen05.ld.32x32b.x32 chunks of 16 doubles.  s >= 256 (58 doubles)
 // sits in this lane's 464-B shared-memory row (29 x 16 B: odd, bank-conflict-free LDS.128).
-constexpr int kWarpsPerCta = 4;                       // warp w owns TMEM lanes 32w..32w+31
+//
+// Two CTA layouts (template parameter WARPS of the episode kernel):
+//   4 warps: one warp per SM sub-partition, every lane owns its whole TMEM lane (256 doubles) + a 464-B row;
+//   5 warps (-DLD_LAYOUT5, measured dead end): warps 0 and 4 SHARE sub-partition 0 — each owns half of its TMEM lanes
+//            (columns 0..255 / 256..511, 128 doubles) and keeps the other 186 doubles in a 1488-B shared-memory row
+//            (93 x 16 B, odd) — while warps 1..3 keep the 4-warp layout.  160 brains are all that Tensor Memory + shared
+//            memory of an SM hold (256 KiB + 227 KiB = 192 brains minus the staging buffers).  The two warps do hide each
+//            other's stalls, but a sub-partition takes only ~40 B/clk from shared memory: 3,642 cycles per step for each of
+//            the two against 2,000 for a warp alone — the SM's rate is unchanged and 40 % of the lanes fly at half speed
+//            (65,536 survivors: 8.02 ms against 6.85 ms; DESIGN.md 4, scripts/layout_probe.py).
+constexpr int kWarpsPerCta = 4;                       // the default layout: warp w owns TMEM lanes 32w..32w+31
 constexpr int kCtaThreads = kWarpsPerCta * 32;        // 128 drones resident per SM
 constexpr int kTmemCols = 512;                        // the whole Tensor Memory of the SM
-constexpr int kTmemDoubles = kTmemCols / 2;           // 256 weights per lane
 constexpr int kChunk = 16;                            // doubles per tcgen05.ld x32
-constexpr int kChunks = kTmemDoubles / kChunk;        // 16
-constexpr int kSmemDoubles = LD_GENOME_LEN - kTmemDoubles; // 58
-constexpr int kRowBytes = kSmemDoubles * 8;           // 464
-constexpr int kSmemUsed = kCtaThreads * kRowBytes;    // 59392
+// where one lane's brain lives: TM doubles in Tensor Memory (stored index s < TM), the rest in its shared-memory row
+template <int TM>
+struct BrainLay {
+    static constexpr int kTm = TM;                       // 256 (whole TMEM lane) or 128 (half)
+    static constexpr int kChunks = TM / kChunk;          // 16 or 8 tcgen05.ld x32 per step
+    static constexpr int kSm = LD_GENOME_LEN - TM;       // 58 or 186
+    static constexpr int kRowBytes = kSm * 8;            // 464 or 1488
+    static_assert(TM % kChunk == 0 && kSm % 2 == 0, "whole chunks, double2 rows");
+    static_assert((kRowBytes / 16) % 2 == 1, "row stride must be an odd number of 16-B units (bank-conflict-free LDS.128)");
+};
 // Brain staging: the rows of the lanes that get a new drone are copied into a per-warp staging buffer with
 // coalesced 16-B cp.async (a 2512-B row = 157 pieces), kStageRows rows at a time; the owner lanes then read their
 // row in stored order (the genome -> stored permutation costs nothing at LDS time; rows 2512 B apart are
@@ -50,24 +65,32 @@ constexpr int kSmemUsed = kCtaThreads * kRowBytes;    // 59392
 #ifndef LD_STAGE_ROWS
 #define LD_STAGE_ROWS 8
 #endif
-constexpr int kStageRows = LD_STAGE_ROWS;
 constexpr int kGenomeBytes = LD_GENOME_LEN * 8;            // 2512
 constexpr int kRowPieces = kGenomeBytes / 16;              // 157
 #ifndef LD_STAGE_BUFFERS
 #define LD_STAGE_BUFFERS 1 // 2 (220 KB of shared memory): the next group's rows arrive while this group's are written — a whole-warp
 #endif                     // hand-over drops from 27.5k to 22-24k cycles, but the headline kernel gets 1.1 % SLOWER (7.08 vs 7.00 ms)
 constexpr int kStageBuffers = LD_STAGE_BUFFERS;
-constexpr int kStageGroupBytes = kStageRows * kGenomeBytes;   // 20096
-constexpr int kStageBytesPerWarp = kStageBuffers * kStageGroupBytes;
 static_assert(kGenomeBytes % 16 == 0 && kRowPieces % 2 == 1, "16-B pieces, odd row stride");
-// Tensor Memory is one allocation per SM: the request is more than half of the SM's shared memory, so a
-// second CTA (e.g. of a concurrent launch on another stream) can never become resident next to us
-constexpr int kSmemBytes = kSmemUsed + kWarpsPerCta * kStageBytesPerWarp; // 139776
-static_assert(kSmemBytes > 116 * 1024 && kSmemBytes <= 227 * 1024, "one CTA per SM");
-static_assert(kSmemUsed <= kSmemBytes, "shared-memory rows");
+template <int WARPS>
+struct CtaLay {
+    static_assert(WARPS == 4 || WARPS == 5, "layouts");
+    static constexpr int kWarps = WARPS;
+    static constexpr int kThreads = WARPS * 32;
+    static constexpr int kHalfWarps = WARPS == 5 ? 2 : 0; // warps 0 and 4 (both on SM sub-partition 0)
+    static constexpr int kHalfRowsBytes = kHalfWarps * 32 * BrainLay<128>::kRowBytes;
+    static constexpr int kRowsBytes = kHalfRowsBytes + (WARPS - kHalfWarps) * 32 * BrainLay<256>::kRowBytes; // 59392 / 139776
+    static constexpr int kStageRows = WARPS == 5 ? 6 : LD_STAGE_ROWS;
+    static constexpr int kStageGroupBytes = kStageRows * kGenomeBytes;   // 20096 / 15072
+    static constexpr int kStageBytesPerWarp = kStageBuffers * kStageGroupBytes;
+    // Tensor Memory is one allocation per SM: the request is more than half of the SM's shared memory, so a
+    // second CTA (e.g. of a concurrent launch on another stream) can never become resident next to us
+    static constexpr int kSmemBytes = kRowsBytes + WARPS * kStageBytesPerWarp; // 139776 / 215136
+    static_assert(kSmemBytes > 116 * 1024 && kSmemBytes <= 227 * 1024, "one CTA per SM");
+    __host__ __device__ static constexpr bool half(unsigned warp) { return WARPS == 5 && (warp == 0 || warp == 4); }
+};
+constexpr int kSmemBytes = CtaLay<4>::kSmemBytes;
 constexpr int kRefillBatch = 6;                       // idle lanes that trigger a refill
-static_assert((kRowBytes / 16) % 2 == 1, "row stride must be an odd number of 16-B units (bank-conflict-free LDS.128)");
-static_assert(kSmemDoubles % 2 == 0, "double2 staging");
 
 __host__ __device__ constexpr int stored_to_genome(int s) {
     return s < kL1 ? (s % kH1) * (kIn + 1) + s / kH1
@@ -320,29 +343,30 @@ __device__ __forceinline__ void mlp_chunk(Mlp& m, const uint32_t (&v)[32]) {
     }
 }
 
-template <int P = 0>
+template <int TM, int P = 0>
 __device__ __forceinline__ void mlp_smem_tail(Mlp& m, const double2* __restrict__ wrow) {
-    if constexpr (P < kSmemDoubles / 2) {
+    if constexpr (P < BrainLay<TM>::kSm / 2) {
         const double2 w = wrow[P];
-        mlp_mac<kTmemDoubles + 2 * P>(m, w.x);
-        mlp_mac<kTmemDoubles + 2 * P + 1>(m, w.y);
-        mlp_smem_tail<P + 1>(m, wrow);
+        mlp_mac<TM + 2 * P>(m, w.x);
+        mlp_mac<TM + 2 * P + 1>(m, w.y);
+        mlp_smem_tail<TM, P + 1>(m, wrow);
     }
 }
 
 // chunks C..15 with the next TWO chunks' tcgen05.ld in flight while chunk C is consumed (`cur` holds chunk C,
 // `nxt` was requested one chunk ago, `nx2` is free)
-template <int C>
+template <int TM, int C>
 __device__ __forceinline__ void mlp_tmem_chunks(Mlp& m, uint32_t taddr, uint32_t (&cur)[32], uint32_t (&nxt)[32], uint32_t (&nx2)[32]) {
-    if constexpr (C + 2 < kChunks) tmem_ld32(nx2, taddr + 32 * (C + 2));
+    if constexpr (C + 2 < BrainLay<TM>::kChunks) tmem_ld32(nx2, taddr + 32 * (C + 2));
     mlp_chunk<C>(m, cur);
-    if constexpr (C + 1 < kChunks) {
+    if constexpr (C + 1 < BrainLay<TM>::kChunks) {
         tmem_wait_ld(nxt);
-        mlp_tmem_chunks<C + 1>(m, taddr, nxt, nx2, cur);
+        mlp_tmem_chunks<TM, C + 1>(m, taddr, nxt, nx2, cur);
     }
 }
 
 // evolve/brain.py:56-76 on this lane's staged weights (warp-converged: tcgen05.ld is .sync.aligned)
+template <int TM>
 __device__ __forceinline__ void brain(Drone& d, uint32_t taddr, const double2* __restrict__ wrow, double neg_beta, bool keep_old,
                                       uint32_t (&a)[32]) {
     Mlp m;
@@ -358,8 +382,8 @@ __device__ __forceinline__ void brain(Drone& d, uint32_t taddr, const double2* _
     uint32_t b[32], c[32];
     tmem_ld32(b, taddr + 32);
     tmem_wait_ld(a);
-    mlp_tmem_chunks<0>(m, taddr, a, b, c);
-    mlp_smem_tail(m, wrow);
+    mlp_tmem_chunks<TM, 0>(m, taddr, a, b, c);
+    mlp_smem_tail<TM>(m, wrow);
 #pragma unroll
     for (int j = 0; j < kOut; ++j) {
         const double th = sigmoid_fast(m.out[j], neg_beta);
@@ -406,9 +430,9 @@ __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.w
 // the waits and the LDS latency are paid four times instead of sixteen.  `mine` = this lane's staged row (genome
 // order) if it is in the group.  Warp-converged.
 constexpr int kStageBatch = 2; // 4 spills the hot loop's registers (255 + 1.5 KB of spill stores): measured 30 % slower
-template <int C0 = 0>
+template <int TM, int C0 = 0>
 __device__ __forceinline__ void stage_tmem(uint32_t taddr, bool in_group, const double* __restrict__ mine) {
-    if constexpr (C0 < kChunks) {
+    if constexpr (C0 < BrainLay<TM>::kChunks) {
         uint32_t v[kStageBatch][32];
 #pragma unroll
         for (int q = 0; q < kStageBatch; ++q) tmem_ld32(v[q], taddr + 32 * (C0 + q));
@@ -428,37 +452,24 @@ __device__ __forceinline__ void stage_tmem(uint32_t taddr, bool in_group, const 
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < kStageBatch; ++q) tmem_st32(v[q], taddr + 32 * (C0 + q));
-        stage_tmem<C0 + kStageBatch>(taddr, in_group, mine);
+        stage_tmem<TM, C0 + kStageBatch>(taddr, in_group, mine);
     }
 }
-static_assert(kChunks % kStageBatch == 0, "staging rounds");
+static_assert(BrainLay<256>::kChunks % kStageBatch == 0 && BrainLay<128>::kChunks % kStageBatch == 0, "staging rounds");
 
 // One population evaluation = the loop of evolve/evolution.py:64-73 around flight/__init__.py:fly().
 // MODE kState: also write the final kinematic state; kTrace: n == 1, dump the state after every
 // measure() (debug tap).  All 32 lanes execute every step (idle lanes run masked) so that the
 // step body is one straight-line, warp-converged block.
-template <bool EXTRAS, int MODE, bool PROF = false>
-__global__ void __launch_bounds__(kCtaThreads, 1)
-fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict__ genomes, long long n,
-                   ld_record* __restrict__ records, double* __restrict__ final_state,
-                   const __grid_constant__ Sched q, double* __restrict__ trace) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint32_t tmem_base_slot;
-    double2* wrow = reinterpret_cast<double2*>(smem_raw + (size_t)threadIdx.x * kRowBytes);
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    unsigned char* stage_buf = smem_raw + kSmemUsed + (size_t)warp * kStageBytesPerWarp; // this warp's kStageRows staged rows
-
-    // the CTA owns the SM's whole Tensor Memory (512 columns x 128 lanes x 32 bit = 256 KiB)
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_slot)));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint32_t tmem_base = tmem_base_slot;
-    const uint32_t taddr = tmem_base + ((warp * 32u) << 16); // this warp's lane quadrant, column 0
-
+// The whole life of one warp of the episode kernel.  TM = this warp's brain layout (BrainLay): `taddr` is the first of its
+// TM/... Tensor-Memory columns in its own lane quadrant, `wrow` this lane's shared-memory row, `stage_buf` the warp's staging
+// buffer.
+template <bool EXTRAS, int MODE, bool PROF, int WARPS, int TM>
+__device__ __forceinline__ void fly_warp(const ld_params& p, const double* __restrict__ genomes, long long n,
+                                         ld_record* __restrict__ records, double* __restrict__ final_state, const Sched& q,
+                                         double* __restrict__ trace, const uint32_t taddr, double2* __restrict__ wrow,
+                                         unsigned char* __restrict__ stage_buf, const unsigned lane, const unsigned warp) {
+    constexpr int kStageRows = CtaLay<WARPS>::kStageRows, kStageGroupBytes = CtaLay<WARPS>::kStageGroupBytes;
     const double neg_beta = -p.sigmoid_beta;
     const double rcp_m = 1.0 / (double)p.m_total32;
     const int time_reward = (p.reward_time ? p.reward_time_passed : 0) - (p.punish_time ? p.reward_time_passed : 0);
@@ -483,8 +494,8 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
     int t = 0, t_end = 0;
     bool more = true; // slots left to claim (warp-uniform)
     // LD_SLICE_STAGGER: the boundary of this warp's first batch, spread evenly over the horizon across the grid's warps
-    const int total_warps = (int)gridDim.x * kWarpsPerCta;
-    int first_boundary = q.stagger ? max(1, (int)(((long long)H * ((long long)blockIdx.x * kWarpsPerCta + warp + 1)) / total_warps)) : 0;
+    const int total_warps = (int)gridDim.x * WARPS;
+    int first_boundary = q.stagger ? max(1, (int)(((long long)H * ((long long)blockIdx.x * WARPS + warp + 1)) / total_warps)) : 0;
 
     for (;;) {
         // ---- claim queue slots for idle lanes (warp-aggregated, batched) ---------------------------
@@ -605,10 +616,10 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
                     stage_buf + (size_t)buf * kStageGroupBytes + (size_t)__popc(group & ((1u << lane) - 1u)) * kGenomeBytes);
                 if (in_group) {
 #pragma unroll
-                    for (int i = 0; i < kSmemDoubles / 2; ++i)
-                        wrow[i] = make_double2(mine[stored_to_genome(kTmemDoubles + 2 * i)], mine[stored_to_genome(kTmemDoubles + 2 * i + 1)]);
+                    for (int i = 0; i < BrainLay<TM>::kSm / 2; ++i)
+                        wrow[i] = make_double2(mine[stored_to_genome(TM + 2 * i)], mine[stored_to_genome(TM + 2 * i + 1)]);
                 }
-                stage_tmem(taddr, in_group, mine);
+                stage_tmem<TM>(taddr, in_group, mine);
                 __syncwarp(); // everyone is done with this buffer before it is requested again
                 if (PROF) {
                     const long long now_ = clock64();
@@ -688,7 +699,7 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
             // next step's trigonometry and this step's brain: independent, one basic block, interleaved
             // by the scheduler
             trig_fast(d);
-            brain(d, taddr, wrow, neg_beta, MODE != kPlain && crashed, w0);
+            brain<TM>(d, taddr, wrow, neg_beta, MODE != kPlain && crashed, w0);
             if (MODE == kTrace) {
                 if (live && !crashed) {
 #pragma unroll
@@ -753,6 +764,41 @@ fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict
 #pragma unroll
             for (int i = 0; i < kProfCount; ++i) atomicAdd(q.prof + i, pf[i]);
         }
+    }
+}
+
+template <bool EXTRAS, int MODE, bool PROF = false, int WARPS = 4>
+__global__ void __launch_bounds__(CtaLay<WARPS>::kThreads, 1)
+fly_mlp_f64_kernel(const __grid_constant__ ld_params p, const double* __restrict__ genomes, long long n,
+                   ld_record* __restrict__ records, double* __restrict__ final_state,
+                   const __grid_constant__ Sched q, double* __restrict__ trace) {
+    using L = CtaLay<WARPS>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t tmem_base_slot;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned char* stage_buf = smem_raw + L::kRowsBytes + (size_t)warp * L::kStageBytesPerWarp; // this warp's kStageRows staged rows
+
+    // the CTA owns the SM's whole Tensor Memory (512 columns x 128 lanes x 32 bit = 256 KiB)
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = tmem_base_slot;
+    // a warp can only reach the TMEM lanes of its own SM sub-partition (warp % 4)
+    const uint32_t quadrant = tmem_base + (((warp & 3u) * 32u) << 16);
+    if (L::half(warp)) {
+        // warps 0 and 4 share sub-partition 0: columns 0..255 / 256..511 of lanes 0..31; rows of 1488 B at the start
+        unsigned char* row = smem_raw + (size_t)((warp == 4 ? 32u : 0u) + lane) * BrainLay<128>::kRowBytes;
+        fly_warp<EXTRAS, MODE, PROF, WARPS, 128>(p, genomes, n, records, final_state, q, trace, quadrant + (warp == 4 ? 256u : 0u),
+                                                 reinterpret_cast<double2*>(row), stage_buf, lane, warp);
+    } else {
+        const unsigned full_index = WARPS == 5 ? (warp - 1u) * 32u + lane : threadIdx.x;
+        unsigned char* row = smem_raw + L::kHalfRowsBytes + (size_t)full_index * BrainLay<256>::kRowBytes;
+        fly_warp<EXTRAS, MODE, PROF, WARPS, 256>(p, genomes, n, records, final_state, q, trace, quadrant, reinterpret_cast<double2*>(row),
+                                                 stage_buf, lane, warp);
     }
 
     // every warp is done with its Tensor-Memory lanes before the allocation is returned
@@ -1382,6 +1428,13 @@ int ensure_device() {
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f64_kernel<false, kTrace>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f64_kernel<true, kTrace>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f64_kernel<false, kPlain, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+#ifdef LD_LAYOUT5
+    LD_CUDA(cudaFuncSetAttribute(fly_mlp_f64_kernel<false, kPlain, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtaLay<5>::kSmemBytes));
+    LD_CUDA(cudaFuncSetAttribute(fly_mlp_f64_kernel<true, kPlain, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtaLay<5>::kSmemBytes));
+    LD_CUDA(cudaFuncSetAttribute(fly_mlp_f64_kernel<false, kState, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtaLay<5>::kSmemBytes));
+    LD_CUDA(cudaFuncSetAttribute(fly_mlp_f64_kernel<true, kState, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtaLay<5>::kSmemBytes));
+    LD_CUDA(cudaFuncSetAttribute(fly_mlp_f64_kernel<false, kPlain, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtaLay<5>::kSmemBytes));
+#endif
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f32_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesF32));
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f32_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesF32));
     LD_CUDA(cudaFuncSetAttribute(fly_mlp_f32_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesF32));
@@ -1396,6 +1449,20 @@ int ensure_device() {
     g_dev.sms = prop.multiProcessorCount;
     g_dev.attrs_set = true;
     return LD_OK;
+}
+
+// CTA layout of the fp64 episode kernel: 4 warps per SM.  The 5-warp layout (top of this file) is a measured dead end
+// that stays reproducible: build with -DLD_LAYOUT5 and run with LD_WARPS_PER_SM=5 (scripts/layout_probe.py).
+int layout_warps() {
+#ifdef LD_LAYOUT5
+    static const int v = [] {
+        const char* e = getenv("LD_WARPS_PER_SM");
+        return (e && atoi(e) == 5) ? 5 : 4;
+    }();
+    return v;
+#else
+    return kWarpsPerCta;
+#endif
 }
 
 bool has_extras(const ld_params* p) {
@@ -1454,9 +1521,11 @@ int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* 
         LD_CUDA(cudaGetLastError());
         return LD_OK;
     }
-    long long ctas = (n + kCtaThreads - 1) / kCtaThreads;
+    const int warps = trace ? 4 : layout_warps(); // the trajectory tap flies one drone: default layout
+    const int cta_threads = warps * 32;
+    long long ctas = (n + cta_threads - 1) / cta_threads;
     if (ctas > g_dev.sms) ctas = g_dev.sms;
-    dim3 grid((unsigned)ctas), block(kCtaThreads);
+    dim3 grid((unsigned)ctas), block(cta_threads);
     const bool ex = has_extras(p);
     const int H = p->timesteps;
     // Episode segments (ld_params.slice_steps): only when drones outnumber the lanes, otherwise nobody ever
@@ -1478,12 +1547,12 @@ int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* 
     const int requested = (p->slice_steps == LD_SLICE_STAGGER && arrived != nullptr) ? 0 : p->slice_steps;
     const bool stagger = requested == LD_SLICE_STAGGER;
     const bool doubling = !stagger && (requested <= -2 || requested == 0);
-    const int slice = stagger ? 0 : (requested == 0 ? auto_first_segment(n, ctas * kCtaThreads, H) : (requested <= -2 ? -requested : requested));
+    const int slice = stagger ? 0 : (requested == 0 ? auto_first_segment(n, ctas * cta_threads, H) : (requested <= -2 ? -requested : requested));
     q.growth = doubling ? 2 : 1;
     void* scratch = nullptr;
-    const bool queue_ok = !trace && n > ctas * kCtaThreads && n < 0x7fffffffLL;
+    const bool queue_ok = !trace && n > ctas * cta_threads && n < 0x7fffffffLL;
     if (queue_ok && stagger && H > 1) {
-        q.cap = ctas * kCtaThreads; // only drones of the first wave are ever parked, once each
+        q.cap = ctas * cta_threads; // only drones of the first wave are ever parked, once each
         q.stagger = 1;              // q.slice stays H: no other boundary
     } else if (queue_ok && slice > 0 && slice < H) {
         long long segments = ((long long)H + slice - 1) / slice;
@@ -1503,12 +1572,23 @@ int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* 
         q.requeue = reinterpret_cast<int*>(q.tail + 2);
         q.park = reinterpret_cast<double*>(static_cast<char*>(scratch) + queue_bytes);
     }
+#define LD_LAUNCH_W(EX, MD, PR, W) \
+    fly_mlp_f64_kernel<EX, MD, PR, W><<<grid, block, CtaLay<W>::kSmemBytes, s>>>(*p, genomes, n, records, final_state, q, trace)
 #define LD_LAUNCH(EX, MD) \
-    fly_mlp_f64_kernel<EX, MD><<<grid, block, kSmemBytes, s>>>(*p, genomes, n, records, final_state, q, trace)
+    LD_LAUNCH_W(EX, MD, false, 4)
     const int mode = trace ? kTrace : (final_state ? kState : kPlain);
     if (prof) {
         if (ex || mode != kPlain) return fail(LD_ERR_INVALID_ARG, "the profile build exists for the plain kernel without wind / payload / final state");
-        fly_mlp_f64_kernel<false, kPlain, true><<<grid, block, kSmemBytes, s>>>(*p, genomes, n, records, final_state, q, trace);
+#ifdef LD_LAYOUT5
+        if (warps == 5) LD_LAUNCH_W(false, kPlain, true, 5);
+        else
+#endif
+            LD_LAUNCH_W(false, kPlain, true, 4);
+#ifdef LD_LAYOUT5
+    } else if (warps == 5) {
+        if (ex) { if (mode == kState) LD_LAUNCH_W(true, kState, false, 5); else LD_LAUNCH_W(true, kPlain, false, 5); }
+        else { if (mode == kState) LD_LAUNCH_W(false, kState, false, 5); else LD_LAUNCH_W(false, kPlain, false, 5); }
+#endif
     } else if (ex) {
         if (mode == kTrace) LD_LAUNCH(true, kTrace);
         else if (mode == kState) LD_LAUNCH(true, kState);
@@ -1519,6 +1599,7 @@ int launch_fly(const ld_params* p, const double* genomes, int64_t n, ld_record* 
         else LD_LAUNCH(false, kPlain);
     }
 #undef LD_LAUNCH
+#undef LD_LAUNCH_W
     cudaError_t launched = cudaGetLastError();
     if (scratch) LD_CUDA(cudaFreeAsync(scratch, s));
     if (launched != cudaSuccess) return fail(LD_ERR_CUDA, "fly_mlp_f64_kernel launch", launched);
@@ -1666,7 +1747,7 @@ int sws_reserve(size_t drones, bool want_state, bool want_init = false) { return
 int fly_streamed_enqueue(StreamWs& w, const ld_params* params, const double* genomes, const double* init_state, int64_t m,
                          ld_record* records, double* final_state) {
     if (w.in_flight) return fail(LD_ERR_INVALID_ARG, "host workspace busy: wait for the submission in flight first");
-    const int64_t wave = (int64_t)g_dev.sms * kCtaThreads;
+    const int64_t wave = (int64_t)g_dev.sms * layout_warps() * 32;
     // chunks: eighths of a wave (2368 drones = 5.9 MB, the first lanes start after ~0.1 ms) until the first
     // wave is in, then half waves (every chunk costs one extra 8-byte copy on the copy engine)
     const int64_t small = wave / 8 > 1024 ? wave / 8 : 1024;
@@ -1832,7 +1913,7 @@ int ld_device_count(void) {
 
 int64_t ld_wave_size(void) {
     if (ensure_device() != LD_OK) return -1;
-    return (int64_t)g_dev.sms * kCtaThreads;
+    return (int64_t)g_dev.sms * layout_warps() * 32;
 }
 
 int ld_fly_mlp_f64_device(const ld_params* params, const double* genomes, int64_t n, ld_record* records,
