@@ -133,6 +133,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t (&v)[32], uint32_t taddr) {
         : "r"(taddr));
 }
 
+// x16 form (8 doubles) for the hot loop's weight stream, see mlp_tmem_stream
+__device__ __forceinline__ void tmem_ld16(uint32_t (&v)[16], uint32_t taddr) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld_all() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // tcgen05.ld is asynchronous: the registers are valid only after wait::ld.  Passing them through
 // the wait as read-write operands gives the compiler a true dependency, so no consumer can be
 // scheduled above it.
@@ -365,10 +374,46 @@ __device__ __forceinline__ void mlp_tmem_chunks(Mlp& m, uint32_t taddr, uint32_t
     }
 }
 
+#ifndef LD_TMEM_X16
+#define LD_TMEM_X16 1
+#endif
+#if LD_TMEM_X16
+// The hot loop's weight stream in x16 loads (8 doubles), one load ahead in the source and NO tcgen05.wait::ld between the
+// loads: tcgen05.wait::ld waits for EVERY outstanding load, so with it only one load can usefully be in flight, and ptxas
+// issues a tcgen05.ld only ~25 statically scheduled cycles before its first use while an x32 load takes ~35 cycles to land
+// — with one warp per scheduler that was ~155 stalled cycles per warp-step.  Without the wait ptxas tracks every load on a
+// hardware scoreboard of its own (it alternates two), puts the scoreboard wait on the load's first consumer itself, and two
+// x16 loads (~27 cycles each) overlap.  PTX asks for a wait::ld between a tcgen05.ld and the use of its registers; what is
+// executed is SASS, so the build VERIFIES the property on the SASS of every episode-kernel instantiation
+// (build.verify_tmem_scoreboards: between a tcgen05.ld and the first instruction that waits on its scoreboard nothing
+// touches its destination registers) and refuses the library otherwise; the bit-exact parity tests run on top of that.
+// One real wait::ld closes every step's stream.
+typedef uint32_t TmemChunk[16];
+constexpr int kLoadDoubles = 8;
+template <int C, int E = 0>
+__device__ __forceinline__ void mlp_load_chunk(Mlp& m, const uint32_t (&v)[16]) {
+    if constexpr (E < kLoadDoubles) {
+        mlp_mac<C * kLoadDoubles + E>(m, __hiloint2double((int)v[2 * E + 1], (int)v[2 * E]));
+        mlp_load_chunk<C, E + 1>(m, v);
+    }
+}
+template <int TM, int C>
+__device__ __forceinline__ void mlp_tmem_stream(Mlp& m, uint32_t taddr, uint32_t (&cur)[16], uint32_t (&nxt)[16]) {
+    constexpr int kLoads = TM / kLoadDoubles;
+    if constexpr (C + 1 < kLoads) tmem_ld16(nxt, taddr + 16 * (C + 1));
+    mlp_load_chunk<C>(m, cur);
+    if constexpr (C + 1 < kLoads) mlp_tmem_stream<TM, C + 1>(m, taddr, nxt, cur);
+}
+__device__ __forceinline__ void tmem_ld_first(TmemChunk& v, uint32_t taddr) { tmem_ld16(v, taddr); }
+#else
+typedef uint32_t TmemChunk[32];
+__device__ __forceinline__ void tmem_ld_first(TmemChunk& v, uint32_t taddr) { tmem_ld32(v, taddr); }
+#endif
+
 // evolve/brain.py:56-76 on this lane's staged weights (warp-converged: tcgen05.ld is .sync.aligned)
 template <int TM>
 __device__ __forceinline__ void brain(Drone& d, uint32_t taddr, const double2* __restrict__ wrow, double neg_beta, bool keep_old,
-                                      uint32_t (&a)[32]) {
+                                      TmemChunk& a) {
     Mlp m;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -379,11 +424,18 @@ __device__ __forceinline__ void brain(Drone& d, uint32_t taddr, const double2* _
         m.in[12 + i] = d.coin[i];
     }
     // chunk 0 was requested before the physics of this step (its latency hides behind it)
+#if LD_TMEM_X16
+    TmemChunk b;
+    mlp_tmem_stream<TM, 0>(m, taddr, a, b);
+    mlp_smem_tail<TM>(m, wrow);
+    tmem_wait_ld_all(); // nothing is in flight any more: every chunk's consumers have waited on its scoreboard
+#else
     uint32_t b[32], c[32];
     tmem_ld32(b, taddr + 32);
     tmem_wait_ld(a);
     mlp_tmem_chunks<TM, 0>(m, taddr, a, b, c);
     mlp_smem_tail<TM>(m, wrow);
+#endif
 #pragma unroll
     for (int j = 0; j < kOut; ++j) {
         const double th = sigmoid_fast(m.out[j], neg_beta);
@@ -686,8 +738,8 @@ __device__ __forceinline__ void fly_warp(const ld_params& p, const double* __res
         do {
             int u;
             if (PROF) ++prof_iters;
-            uint32_t w0[32];
-            tmem_ld32(w0, taddr); // first 16 brain weights for this step's MLP, in flight during the physics
+            TmemChunk w0;
+            tmem_ld_first(w0, taddr); // first brain weights for this step's MLP, in flight during the physics
             step_rewards_and_coin(p, d, live, time_reward);
             crashed = physics_step<EXTRAS>(p, d, rcp_m, MODE != kPlain ? a_last : nullptr, u, dt_lane) && live;
             d.reward += crashed ? p.reward_crashed : ((live ? u : 0) * p.reward_unstable);

@@ -11,7 +11,11 @@
 //   VARIANT 1: one load ahead, chunk = NREG registers (16 / 32 / 64)
 //   VARIANT 2: as 1, with __syncwarp() after every load's issue (is it a scheduling fence?)
 //   VARIANT 3: as 1, the next chunk's load issued behind an opaque never-taken branch (basic-block boundary)
-//   VARIANT 4: latency probe: ld; wait; consume; next address depends on the data (NREG = 8..128)
+//   VARIANT 5: as 1 (x32), with 4 shared-memory-fed fma (2 LDS.128) between consecutive Tensor-Memory chunks — the
+//              brain's shared-memory part spread between the chunks instead of behind them
+//   VARIANT 6: as 1 without tcgen05.wait::ld between the chunks (timing / SASS study only — PTX requires the wait): ptxas
+//              still puts a scoreboard wait on every first consumer, and alternates two scoreboards for x16 loads
+//   latency probe: ld; wait; consume; next address depends on the data (NREG = 8..128)
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -77,6 +81,9 @@ __device__ __forceinline__ void consume(const Regs<N>& r, double (&acc)[10], con
     }
 }
 
+__shared__ __align__(16) unsigned char g_rows[128 * 272]; // 17 x 16 B per lane (odd: conflict-free LDS.128)
+__device__ __forceinline__ const unsigned char* never_row(int never) { return g_rows + (threadIdx.x + never) * 272; }
+
 template <int N, int C, int VARIANT>
 struct Stream {
     static constexpr int kChunks = 512 / N;
@@ -89,6 +96,22 @@ struct Stream {
                 tmem_wait();
                 Stream<N, C + 1, VARIANT>::run(taddr, nxt, nx2, cur, acc, in, never);
             }
+        } else if constexpr (VARIANT == 5) {
+            if constexpr (C + 1 < kChunks) tmem_ld<N>(nxt, taddr + N * (C + 1));
+            consume<N, C * (N / 2 + 4)>(cur, acc, in);
+            {
+                const double2* row = reinterpret_cast<const double2*>(never_row(never));
+                const double2 w0 = row[(2 * C) % 16], w1 = row[(2 * C + 1) % 16];
+                constexpr int B = C * (N / 2 + 4) + N / 2;
+                acc[(B + 0) % 10] = fma(w0.x, in[((B + 0) / 10) % 16], acc[(B + 0) % 10]);
+                acc[(B + 1) % 10] = fma(w0.y, in[((B + 1) / 10) % 16], acc[(B + 1) % 10]);
+                acc[(B + 2) % 10] = fma(w1.x, in[((B + 2) / 10) % 16], acc[(B + 2) % 10]);
+                acc[(B + 3) % 10] = fma(w1.y, in[((B + 3) / 10) % 16], acc[(B + 3) % 10]);
+            }
+            if constexpr (C + 1 < kChunks) {
+                tmem_wait();
+                Stream<N, C + 1, VARIANT>::run(taddr, nxt, cur, nx2, acc, in, never);
+            }
         } else {
             if constexpr (C + 1 < kChunks) {
                 if (VARIANT == 3) {
@@ -99,7 +122,7 @@ struct Stream {
             }
             consume<N, C * (N / 2)>(cur, acc, in);
             if constexpr (C + 1 < kChunks) {
-                tmem_wait();
+                if (VARIANT != 6) tmem_wait(); // 6: no tcgen05.wait::ld between the chunks (what does ptxas do on its own?)
                 Stream<N, C + 1, VARIANT>::run(taddr, nxt, cur, nx2, acc, in, never);
             }
         }
@@ -118,6 +141,10 @@ __global__ void __launch_bounds__(128, 1) stream_bench(double* out, long long* c
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t taddr = holder + ((uint32_t)(warp * 32) << 16);
+    if (VARIANT == 5) {
+        for (int i = threadIdx.x; i < 128 * 272 / 8; i += blockDim.x) reinterpret_cast<double*>(g_rows)[i] = 1e-3 * i;
+        __syncthreads();
+    }
     double acc[10], in[16];
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] = 0.0;
@@ -198,6 +225,9 @@ int main() {
     RUN(16, 2, "(one ahead + __syncwarp after the issue)")
     RUN(32, 2, "(one ahead + __syncwarp after the issue)")
     RUN(64, 2, "(one ahead + __syncwarp after the issue)")
+    RUN(32, 5, "(one ahead + 4 smem-fed fma between chunks; 320 fma, floor 640)")
+    RUN(16, 6, "(one ahead, NO wait::ld between chunks: timing only)")
+    RUN(32, 6, "(one ahead, NO wait::ld between chunks: timing only)")
     RUN(16, 3, "(one ahead, issue behind an opaque branch)")
     RUN(32, 3, "(one ahead, issue behind an opaque branch)")
     RUN(64, 3, "(one ahead, issue behind an opaque branch)")
