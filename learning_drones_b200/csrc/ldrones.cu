@@ -6,8 +6,9 @@
 //   * each lane's brain (314 fp64 weights) must be re-read every timestep and nothing else is
 //     (measured: ~40 B/clk/warp from shared memory, ~54 B/clk/warp from Tensor Memory).  256 weights
 //     per lane therefore sit in Tensor Memory (all 512 columns of the lane) and are streamed with
-//     tcgen05.ld, 58 in the lane's shared-memory row; what binds is the fp64 pipe + dependency
-//     latency of the one warp a sub-partition has room for.
+//     tcgen05.ld (x16 loads on alternating scoreboards, no wait::ld between them: mlp_tmem_stream), 58 in
+//     the lane's shared-memory row; what binds is the fp64 pipe + dependency latency of the one warp a
+//     sub-partition has room for.
 //   * long episodes are flown in segments: at a segment boundary a drone whose lane is wanted by
 //     a waiting drone is parked in HBM and re-queued (round robin), so a population of survivors
 //     ends together instead of in whole-episode waves (struct Sched).
@@ -32,8 +33,9 @@ using namespace ld;
 //   s in [160,270) : layer 2, s-160 = k*10 + j  <-> genome[160 + j*11 + k]
 //   s in [270,314) : layer 3, s-270 = k*4 + j   <-> genome[270 + j*11 + k]
 // s < 256 sits in Tensor Memory: lane = the thread's TMEM lane, columns 2s (low word), 2s+1 (high
-// word); read per step as 16 tcgen05.ld.32x32b.x32 chunks of 16 doubles.  s >= 256 (58 doubles)
-// sits in this lane's 464-B shared-memory row (29 x 16 B: odd, bank-conflict-free LDS.128).
+// word); read per step as 32 tcgen05.ld.32x32b.x16 loads of 8 doubles (staging writes and re-reads it in
+// x32 chunks of 16).  s >= 256 (58 doubles) sits in this lane's 464-B shared-memory row (29 x 16 B: odd,
+// bank-conflict-free LDS.128).
 //
 // Two CTA layouts (template parameter WARPS of the episode kernel):
 //   4 warps: one warp per SM sub-partition, every lane owns its whole TMEM lane (256 doubles) + a 464-B row;
@@ -47,12 +49,12 @@ using namespace ld;
 constexpr int kWarpsPerCta = 4;                       // the default layout: warp w owns TMEM lanes 32w..32w+31
 constexpr int kCtaThreads = kWarpsPerCta * 32;        // 128 drones resident per SM
 constexpr int kTmemCols = 512;                        // the whole Tensor Memory of the SM
-constexpr int kChunk = 16;                            // doubles per tcgen05.ld x32
+constexpr int kChunk = 16;                            // doubles per tcgen05.ld / tcgen05.st x32 (staging)
 // where one lane's brain lives: TM doubles in Tensor Memory (stored index s < TM), the rest in its shared-memory row
 template <int TM>
 struct BrainLay {
     static constexpr int kTm = TM;                       // 256 (whole TMEM lane) or 128 (half)
-    static constexpr int kChunks = TM / kChunk;          // 16 or 8 tcgen05.ld x32 per step
+    static constexpr int kChunks = TM / kChunk;          // 16 or 8 x32 chunks
     static constexpr int kSm = LD_GENOME_LEN - TM;       // 58 or 186
     static constexpr int kRowBytes = kSm * 8;            // 464 or 1488
     static_assert(TM % kChunk == 0 && kSm % 2 == 0, "whole chunks, double2 rows");
@@ -344,14 +346,6 @@ __device__ __forceinline__ void mlp_mac(Mlp& m, double w) {
     }
 }
 
-template <int C, int E = 0>
-__device__ __forceinline__ void mlp_chunk(Mlp& m, const uint32_t (&v)[32]) {
-    if constexpr (E < kChunk) {
-        mlp_mac<C * kChunk + E>(m, __hiloint2double((int)v[2 * E + 1], (int)v[2 * E]));
-        mlp_chunk<C, E + 1>(m, v);
-    }
-}
-
 template <int TM, int P = 0>
 __device__ __forceinline__ void mlp_smem_tail(Mlp& m, const double2* __restrict__ wrow) {
     if constexpr (P < BrainLay<TM>::kSm / 2) {
@@ -359,18 +353,6 @@ __device__ __forceinline__ void mlp_smem_tail(Mlp& m, const double2* __restrict_
         mlp_mac<TM + 2 * P>(m, w.x);
         mlp_mac<TM + 2 * P + 1>(m, w.y);
         mlp_smem_tail<TM, P + 1>(m, wrow);
-    }
-}
-
-// chunks C..15 with the next TWO chunks' tcgen05.ld in flight while chunk C is consumed (`cur` holds chunk C,
-// `nxt` was requested one chunk ago, `nx2` is free)
-template <int TM, int C>
-__device__ __forceinline__ void mlp_tmem_chunks(Mlp& m, uint32_t taddr, uint32_t (&cur)[32], uint32_t (&nxt)[32], uint32_t (&nx2)[32]) {
-    if constexpr (C + 2 < BrainLay<TM>::kChunks) tmem_ld32(nx2, taddr + 32 * (C + 2));
-    mlp_chunk<C>(m, cur);
-    if constexpr (C + 1 < BrainLay<TM>::kChunks) {
-        tmem_wait_ld(nxt);
-        mlp_tmem_chunks<TM, C + 1>(m, taddr, nxt, nx2, cur);
     }
 }
 
@@ -406,8 +388,26 @@ __device__ __forceinline__ void mlp_tmem_stream(Mlp& m, uint32_t taddr, uint32_t
 }
 __device__ __forceinline__ void tmem_ld_first(TmemChunk& v, uint32_t taddr) { tmem_ld16(v, taddr); }
 #else
+// -DLD_TMEM_X16=0: the stream of the first half of round 2 (profiles/r02_b_*), kept for A/B runs: x32 loads, three rotating
+// buffers, a wait::ld before every chunk (chunks C..15 with the next two chunks' loads requested while chunk C is consumed)
 typedef uint32_t TmemChunk[32];
 __device__ __forceinline__ void tmem_ld_first(TmemChunk& v, uint32_t taddr) { tmem_ld32(v, taddr); }
+template <int C, int E = 0>
+__device__ __forceinline__ void mlp_chunk(Mlp& m, const uint32_t (&v)[32]) {
+    if constexpr (E < kChunk) {
+        mlp_mac<C * kChunk + E>(m, __hiloint2double((int)v[2 * E + 1], (int)v[2 * E]));
+        mlp_chunk<C, E + 1>(m, v);
+    }
+}
+template <int TM, int C>
+__device__ __forceinline__ void mlp_tmem_chunks(Mlp& m, uint32_t taddr, uint32_t (&cur)[32], uint32_t (&nxt)[32], uint32_t (&nx2)[32]) {
+    if constexpr (C + 2 < BrainLay<TM>::kChunks) tmem_ld32(nx2, taddr + 32 * (C + 2));
+    mlp_chunk<C>(m, cur);
+    if constexpr (C + 1 < BrainLay<TM>::kChunks) {
+        tmem_wait_ld(nxt);
+        mlp_tmem_chunks<TM, C + 1>(m, taddr, nxt, nx2, cur);
+    }
+}
 #endif
 
 // evolve/brain.py:56-76 on this lane's staged weights (warp-converged: tcgen05.ld is .sync.aligned)
