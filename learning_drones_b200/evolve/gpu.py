@@ -52,9 +52,15 @@ class GpuEvolution:
         slice_steps = fly_kw.pop("slice_steps", None)
         self.params = make_params(timesteps=timesteps, **fly_kw)
         # Scheduling only (ld_params.slice_steps).  Offspring populations mix a few long-lived drones with many
-        # that crash early: always fly them in doubling segments (boundaries H/4, 3H/4), also where the library's
-        # automatic rule — which has to assume that every drone may survive — would not bother.
-        self.params.slice_steps = -max(125, timesteps // 4) if slice_steps is None else int(slice_steps)
+        # that crash early: fly them in doubling segments (boundaries H/4, 3H/4), also where the library's
+        # automatic rule — which has to assume that every drone may survive — would not bother (+4 % generations/s
+        # on populations with survivors).  While NO drone reaches the horizon (a young population: the whole of
+        # BASELINE config 5's first generations) the segment queue only costs (-2.3 % generations/s, measured at
+        # 131,072 drones): run() switches it off for the next block of generations whenever the last generation it
+        # has read back had no survivor, and back on otherwise (_adapt_schedule).
+        self._doubling = -max(125, timesteps // 4)
+        self._adaptive_schedule = slice_steps is None
+        self.params.slice_steps = self._doubling if slice_steps is None else int(slice_steps)
         self.seed, self.generation = int(seed), 0
         self.hyper = dict(p_tournament=p_tournament, p_crossover=p_crossover, mutation_rate=mutation_rate, mutation_sigma=mutation_sigma)
         # best-of-run tracking lives on the device (ld_track_best_device): {score, valid}, the genome, and one
@@ -163,7 +169,15 @@ class GpuEvolution:
         for g in range(n_generations):
             self._enqueue_generation(history[g])
         self._history = torch.cat([self._history, history])
-        return [self._history_dict(r) for r in history.cpu().tolist()]
+        rows = [self._history_dict(r) for r in history.cpu().tolist()]
+        self._adapt_schedule(rows)
+        return rows
+
+    def _adapt_schedule(self, rows):
+        """Episode segments for the next block of generations only if the last one had a survivor (scheduling only:
+        results do not depend on it)."""
+        if self._adaptive_schedule and rows:
+            self.params.slice_steps = -1 if rows[-1]["crashed"] >= self.n else self._doubling
 
     def step(self):
         return self.run(1)[0]

@@ -242,3 +242,30 @@ def test_sharded_evolution_loop_on_one_gpu(world):
     assert ha == hb
     assert np.array_equal(a.gather_population(), b.gather_population())
     assert np.array_equal(a.best_genome(), b.best_genome())
+
+
+def test_evolution_schedule_adapts_and_never_changes_results():
+    """GpuEvolution flies without episode segments while no drone of the last generation it read back survived, with the
+    doubling schedule otherwise (evolve/gpu.py, _adapt_schedule) — scheduling only: the generations are bit-identical to
+    a run with a fixed schedule."""
+    from learning_drones_b200.evolve.gpu import GpuEvolution
+
+    rng = np.random.default_rng(5)
+    n, H = 4096, 600
+    young = np.concatenate([rng.normal(0.0, 1.0 / np.sqrt(r), size=(n, r * c)) for r, c in ((10, 16), (10, 11), (4, 11))], axis=1)
+    adaptive = GpuEvolution(young, seed=3, timesteps=H)
+    fixed = GpuEvolution(young, seed=3, timesteps=H, slice_steps=-150)
+    assert adaptive.params.slice_steps == -150  # doubling from H/4 until something is known about the population
+    a = adaptive.run(2) + adaptive.run(3)
+    b = fixed.run(2) + fixed.run(3)
+    assert a == b
+    assert np.array_equal(adaptive.population.cpu().numpy(), fixed.population.cpu().numpy())
+    assert fixed.params.slice_steps == -150
+    assert adaptive.params.slice_steps == (-1 if a[-1]["crashed"] >= n else -150)
+    # a population with survivors switches the segments back on
+    hover = np.zeros((n, GENOME_LEN))
+    hover[:, 270 + 10::11] = np.log(0.1962 / 0.8038) / 0.4  # output-layer bias column: hover thrust
+    adaptive2 = GpuEvolution(hover, seed=3, timesteps=H)
+    adaptive2.params.slice_steps = -1
+    h = adaptive2.run(1)
+    assert h[-1]["crashed"] < n and adaptive2.params.slice_steps == -150
